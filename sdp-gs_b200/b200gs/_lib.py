@@ -1,0 +1,114 @@
+"""ctypes binding of libb200gs.so (the C-ABI declared in include/b200gs.h).
+
+There is no CPU or PyTorch fallback: if the shared library is missing or its ABI does not match
+this binding, importing fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200gs.so")
+
+c_float_p = C.c_void_p  # device pointers are passed as integers
+
+
+class View(C.Structure):
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32),
+        ("tan_fovx", C.c_float), ("tan_fovy", C.c_float),
+        ("scale_modifier", C.c_float),
+        ("sh_degree", C.c_int32), ("sh_coeffs", C.c_int32),
+        ("prefiltered", C.c_int32), ("debug", C.c_int32), ("extended", C.c_int32),
+        ("background", C.c_void_p), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p),
+    ]
+
+
+class Gaussians(C.Structure):
+    _fields_ = [
+        ("P", C.c_int32),
+        ("means3D", C.c_void_p), ("shs", C.c_void_p), ("colors_precomp", C.c_void_p), ("opacities", C.c_void_p),
+        ("scales", C.c_void_p), ("rotations", C.c_void_p), ("cov3D_precomp", C.c_void_p),
+        ("language_feature_precomp", C.c_void_p), ("shs_language", C.c_void_p), ("confidence", C.c_void_p),
+    ]
+
+
+class Outputs(C.Structure):
+    _fields_ = [("color", C.c_void_p), ("depth", C.c_void_p), ("alpha", C.c_void_p), ("feature", C.c_void_p),
+                ("radii", C.c_void_p)]
+
+
+class Workspace(C.Structure):
+    _fields_ = [("geom", C.c_void_p), ("geom_bytes", C.c_size_t), ("binning", C.c_void_p),
+                ("binning_bytes", C.c_size_t), ("image", C.c_void_p), ("image_bytes", C.c_size_t)]
+
+
+class GradOutputs(C.Structure):
+    _fields_ = [("dL_dcolor", C.c_void_p), ("dL_ddepth", C.c_void_p), ("dL_dalpha", C.c_void_p),
+                ("dL_dfeature", C.c_void_p)]
+
+
+class Grads(C.Structure):
+    _fields_ = [("dL_dmeans3D", C.c_void_p), ("dL_dmeans2D", C.c_void_p), ("dL_dshs", C.c_void_p),
+                ("dL_dcolors", C.c_void_p), ("dL_dopacities", C.c_void_p), ("dL_dscales", C.c_void_p),
+                ("dL_drotations", C.c_void_p), ("dL_dcov3D", C.c_void_p), ("dL_dfeatures", C.c_void_p),
+                ("dL_dshs_language", C.c_void_p), ("scratch", C.c_void_p)]
+
+
+EXPORTS = [
+    "b200gs_version", "b200gs_last_error", "b200gs_geom_bytes", "b200gs_image_bytes", "b200gs_binning_bytes",
+    "b200gs_scratch_bytes", "b200gs_forward_preprocess", "b200gs_forward_render", "b200gs_forward",
+    "b200gs_forward_status", "b200gs_backward", "b200gs_mark_visible", "b200gs_geom_layout",
+    "b200gs_image_layout", "b200gs_binning_layout", "b200gs_debug_sorted_keys", "b200gs_launch_count",
+    "b200gs_abi_sizes",
+]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `make -C sdp-gs_b200/csrc` (or __graft_entry__.build()). "
+            "b200gs has no CPU / PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise ImportError(f"{LIB_PATH} does not export {name}")
+    lib.b200gs_last_error.restype = C.c_char_p
+    for f in ("b200gs_geom_bytes", "b200gs_image_bytes", "b200gs_binning_bytes", "b200gs_scratch_bytes"):
+        getattr(lib, f).restype = C.c_size_t
+    lib.b200gs_geom_bytes.argtypes = [C.c_int32]
+    lib.b200gs_image_bytes.argtypes = [C.c_int32, C.c_int32]
+    lib.b200gs_binning_bytes.argtypes = [C.c_int64]
+    lib.b200gs_scratch_bytes.argtypes = [C.c_int32]
+    lib.b200gs_launch_count.restype = C.c_int64
+    P = C.POINTER
+    lib.b200gs_forward_preprocess.argtypes = [P(View), P(Gaussians), P(Outputs), P(Workspace), C.c_void_p, P(C.c_int64)]
+    lib.b200gs_forward_render.argtypes = [P(View), P(Gaussians), P(Outputs), P(Workspace), C.c_int64, C.c_void_p]
+    lib.b200gs_forward.argtypes = [P(View), P(Gaussians), P(Outputs), P(Workspace), C.c_int64, C.c_void_p]
+    lib.b200gs_forward_status.argtypes = [P(Workspace), C.c_void_p, P(C.c_int64), P(C.c_int32)]
+    lib.b200gs_backward.argtypes = [P(View), P(Gaussians), C.c_void_p, P(Workspace), C.c_int64, P(GradOutputs), P(Grads), C.c_void_p]
+    lib.b200gs_mark_visible.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.b200gs_geom_layout.argtypes = [C.c_int32, P(C.c_int64)]
+    lib.b200gs_image_layout.argtypes = [C.c_int32, C.c_int32, P(C.c_int64)]
+    lib.b200gs_binning_layout.argtypes = [C.c_int32, C.c_int32, C.c_int64, P(C.c_int64)]
+    lib.b200gs_debug_sorted_keys.argtypes = [P(View), C.c_int32, P(Workspace), C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.b200gs_abi_sizes.argtypes = [P(C.c_int64)]
+    sizes = (C.c_int64 * 6)()
+    lib.b200gs_abi_sizes(sizes)
+    mine = [C.sizeof(t) for t in (View, Gaussians, Outputs, Workspace, GradOutputs, Grads)]
+    if list(sizes) != mine:
+        raise ImportError(f"ABI mismatch between {LIB_PATH} {list(sizes)} and this binding {mine}")
+    return lib
+
+
+lib = _load()
+
+
+class B200GSError(RuntimeError):
+    pass
+
+
+def check(code):
+    if code != 0:
+        raise B200GSError(lib.b200gs_last_error().decode("utf-8", "replace"))

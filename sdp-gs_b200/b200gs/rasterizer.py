@@ -1,0 +1,259 @@
+"""PyTorch host side of the b200gs rasterizer: the autograd op behind GaussianRasterizer.
+
+Mirrors `_RasterizeGaussians` of the reference (DGR/diff_gaussian_rasterization/__init__.py:44-155):
+same argument order, same saved state (three opaque byte workspaces + num_rendered), same gradient
+tuple order, the same debug-snapshot behaviour -- but the C++/pybind layer (DGR/rasterize_points.cu)
+is replaced by ctypes calls into the C-ABI of include/b200gs.h, on torch's current CUDA stream.
+PyTorch is only used for device memory, streams and autograd plumbing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import Gaussians, GradOutputs, Grads, Outputs, View, Workspace, check, lib
+
+# When not None: binning capacity (instances) used instead of the reference's blocking D2H read of
+# num_rendered (DGR/cuda_rasterizer/rasterizer_impl.cu:281).  See set_binning_capacity().
+_CAPACITY = None
+
+
+def set_binning_capacity(capacity):
+    """None (default): size the binning workspace exactly, with one 8-byte D2H sync per forward, as the
+    reference does.  int: no host sync; the forward drops instances beyond `capacity` and
+    `last_forward_status()` reports the overflow."""
+    global _CAPACITY
+    _CAPACITY = None if capacity is None else int(capacity)
+
+
+def _ptr(t):
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def _f32c(t, name):
+    if t is None or t.numel() == 0:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (b200gs has no CPU path)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _cpu_deep_copy_tuple(args):
+    return tuple(a.detach().cpu().clone() if isinstance(a, torch.Tensor) else a for a in args)
+
+
+class _State:
+    """What forward leaves behind for backward / inspection."""
+    __slots__ = ("view", "gauss", "keep", "P", "W", "H", "capacity", "num_rendered", "extended")
+
+
+def _build_view(rs, P, M, extended, keep):
+    v = View()
+    v.width, v.height = int(rs.image_width), int(rs.image_height)
+    v.tan_fovx, v.tan_fovy = float(rs.tanfovx), float(rs.tanfovy)
+    v.scale_modifier = float(rs.scale_modifier)
+    v.sh_degree, v.sh_coeffs = int(rs.sh_degree), int(M)
+    v.prefiltered, v.debug, v.extended = int(bool(rs.prefiltered)), int(bool(rs.debug)), int(extended)
+    bg = _f32c(rs.bg, "bg")
+    vm = _f32c(rs.viewmatrix, "viewmatrix")
+    pm = _f32c(rs.projmatrix, "projmatrix")
+    cp = _f32c(rs.campos, "campos")
+    keep.extend([bg, vm, pm, cp])
+    v.background, v.viewmatrix, v.projmatrix, v.campos = bg.data_ptr(), vm.data_ptr(), pm.data_ptr(), cp.data_ptr()
+    return v
+
+
+def _forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, shs_language,
+                  language_feature_precomp, confidence, extended):
+    if means3D.dim() != 2 or means3D.shape[1] != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:57-59
+    dev = means3D.device
+    P = means3D.shape[0]
+    H, W = int(rs.image_height), int(rs.image_width)
+    keep = []
+    means3D = _f32c(means3D, "means3D")
+    sh, colors_precomp = _f32c(sh, "shs"), _f32c(colors_precomp, "colors_precomp")
+    opacities = _f32c(opacities, "opacities")
+    scales, rotations = _f32c(scales, "scales"), _f32c(rotations, "rotations")
+    cov3Ds_precomp = _f32c(cov3Ds_precomp, "cov3D_precomp")
+    shs_language = _f32c(shs_language, "shs_language")
+    language_feature_precomp = _f32c(language_feature_precomp, "language_feature_precomp")
+    confidence = _f32c(confidence, "confidence")
+    M = 0 if sh is None else int(sh.shape[1])  # rasterize_points.cu:83-87
+
+    g = Gaussians()
+    g.P = P
+    g.means3D, g.shs, g.colors_precomp, g.opacities = _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(opacities)
+    g.scales, g.rotations, g.cov3D_precomp = _ptr(scales), _ptr(rotations), _ptr(cov3Ds_precomp)
+    g.language_feature_precomp, g.shs_language, g.confidence = _ptr(language_feature_precomp), _ptr(shs_language), _ptr(confidence)
+    v = _build_view(rs, P, M, extended, keep)
+
+    f32 = dict(dtype=torch.float32, device=dev)
+    color = torch.empty((3, H, W), **f32)
+    radii = torch.empty((P,), dtype=torch.int32, device=dev)
+    depth = alpha = feature = None
+    o = Outputs()
+    o.color, o.radii = color.data_ptr(), _ptr(radii)
+    if extended:
+        depth, alpha, feature = torch.empty((1, H, W), **f32), torch.empty((1, H, W), **f32), torch.empty((3, H, W), **f32)
+        o.depth, o.alpha, o.feature = depth.data_ptr(), alpha.data_ptr(), feature.data_ptr()
+
+    geom = torch.empty((lib.b200gs_geom_bytes(P),), dtype=torch.uint8, device=dev)
+    img = torch.empty((lib.b200gs_image_bytes(W, H),), dtype=torch.uint8, device=dev)
+    ws = Workspace()
+    ws.geom, ws.geom_bytes, ws.image, ws.image_bytes = geom.data_ptr(), geom.numel(), img.data_ptr(), img.numel()
+    stream = _stream()
+    if P == 0:  # rasterize_points.cu:81: nothing is launched for an empty scene, outputs are zeros
+        color.zero_()
+        if extended:
+            depth.zero_(); alpha.zero_(); feature.zero_()
+        binning = torch.empty((0,), dtype=torch.uint8, device=dev)
+        return 0, 0, color, depth, alpha, feature, radii, geom, binning, img
+    if _CAPACITY is None:
+        n = C.c_int64(0)
+        check(lib.b200gs_forward_preprocess(C.byref(v), C.byref(g), C.byref(o), C.byref(ws), stream, C.byref(n)))
+        num_rendered, capacity = int(n.value), int(n.value)
+    else:
+        check(lib.b200gs_forward_preprocess(C.byref(v), C.byref(g), C.byref(o), C.byref(ws), stream, None))
+        num_rendered, capacity = -1, int(_CAPACITY)
+    binning = torch.empty((lib.b200gs_binning_bytes(capacity),), dtype=torch.uint8, device=dev)
+    ws.binning, ws.binning_bytes = binning.data_ptr(), binning.numel()
+    check(lib.b200gs_forward_render(C.byref(v), C.byref(g), C.byref(o), C.byref(ws), C.c_int64(capacity), stream))
+    del keep
+    return num_rendered, capacity, color, depth, alpha, feature, radii, geom, binning, img
+
+
+def _backward_impl(rs, num_rendered, capacity, extended, means3D, sh, colors_precomp, opacities, scales, rotations,
+                   cov3Ds_precomp, shs_language, language_feature_precomp, confidence, radii, geom, binning, img,
+                   g_color, g_depth, g_alpha, g_feature):
+    dev = means3D.device
+    P = means3D.shape[0]
+    keep = []
+    M = 0 if (sh is None or sh.numel() == 0) else int(sh.shape[1])
+    f32 = dict(dtype=torch.float32, device=dev)
+    has = lambda t: t is not None and t.numel() != 0
+    # every buffer is fully written by the kernels (zeros where radii == 0): no torch.zeros fills
+    d_means3D = torch.empty((P, 3), **f32)
+    d_means2D = torch.empty((P, 3), **f32)
+    d_opac = torch.empty((P, 1), **f32)
+    d_sh = torch.empty((P, M, 3), **f32) if has(sh) else None
+    d_colors = torch.empty((P, 3), **f32) if has(colors_precomp) else None
+    d_scales = torch.empty((P, 3), **f32) if has(scales) else None
+    d_rots = torch.empty((P, 4), **f32) if has(rotations) else None
+    d_cov = torch.empty((P, 6), **f32) if has(cov3Ds_precomp) else None
+    d_feat = torch.empty((P, 3), **f32) if (extended and has(language_feature_precomp)) else None
+    d_shl = torch.empty(tuple(shs_language.shape), **f32) if (extended and has(shs_language)) else None
+    if P == 0:
+        return d_means3D, d_means2D, d_sh, d_colors, d_opac, d_scales, d_rots, d_cov, d_shl, d_feat
+    scratch = torch.empty((lib.b200gs_scratch_bytes(P),), dtype=torch.uint8, device=dev)
+
+    g = Gaussians()
+    g.P = P
+    g.means3D, g.shs, g.colors_precomp, g.opacities = _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(opacities)
+    g.scales, g.rotations, g.cov3D_precomp = _ptr(scales), _ptr(rotations), _ptr(cov3Ds_precomp)
+    g.language_feature_precomp, g.shs_language, g.confidence = _ptr(language_feature_precomp), _ptr(shs_language), _ptr(confidence)
+    v = _build_view(rs, P, M, extended, keep)
+    ws = Workspace()
+    ws.geom, ws.geom_bytes, ws.image, ws.image_bytes = geom.data_ptr(), geom.numel(), img.data_ptr(), img.numel()
+    ws.binning, ws.binning_bytes = binning.data_ptr(), binning.numel()
+    go = GradOutputs()
+    gc = _f32c(g_color, "grad color")
+    gd, ga, gf = _f32c(g_depth, "grad depth"), _f32c(g_alpha, "grad alpha"), _f32c(g_feature, "grad feature")
+    go.dL_dcolor, go.dL_ddepth, go.dL_dalpha, go.dL_dfeature = _ptr(gc), _ptr(gd), _ptr(ga), _ptr(gf)
+    gr = Grads()
+    gr.dL_dmeans3D, gr.dL_dmeans2D, gr.dL_dshs, gr.dL_dcolors = _ptr(d_means3D), _ptr(d_means2D), _ptr(d_sh), _ptr(d_colors)
+    gr.dL_dopacities, gr.dL_dscales, gr.dL_drotations, gr.dL_dcov3D = _ptr(d_opac), _ptr(d_scales), _ptr(d_rots), _ptr(d_cov)
+    gr.dL_dfeatures, gr.dL_dshs_language, gr.scratch = _ptr(d_feat), _ptr(d_shl), scratch.data_ptr()
+    check(lib.b200gs_backward(C.byref(v), C.byref(g), radii.data_ptr(), C.byref(ws), C.c_int64(capacity), C.byref(go),
+                              C.byref(gr), _stream()))
+    del keep
+    return d_means3D, d_means2D, d_sh, d_colors, d_opac, d_scales, d_rots, d_cov, d_shl, d_feat
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                shs_language, language_feature_precomp, raster_settings, extended):
+        rs = raster_settings
+        confidence = getattr(rs, "confidence", None)
+        args = (rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, shs_language,
+                language_feature_precomp, confidence, extended)
+        if rs.debug:
+            cpu_args = _cpu_deep_copy_tuple(args[1:])  # copy them before they can be corrupted
+            try:
+                res = _forward_impl(*args)
+            except Exception as ex:
+                torch.save(cpu_args, "snapshot_fw.dump")
+                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                raise ex
+        else:
+            res = _forward_impl(*args)
+        num_rendered, capacity, color, depth, alpha, feature, radii, geom, binning, img = res
+        ctx.raster_settings = rs
+        ctx.num_rendered, ctx.capacity, ctx.extended = num_rendered, capacity, extended
+        ctx.confidence = confidence
+        ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, opacities,
+                              shs_language, language_feature_precomp, geom, binning, img)
+        ctx.mark_non_differentiable(radii)
+        if extended:
+            return color, depth, alpha, feature, radii
+        return color, radii
+
+    @staticmethod
+    def backward(ctx, *grad_outs):
+        rs = ctx.raster_settings
+        (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, opacities, shs_language,
+         language_feature_precomp, geom, binning, img) = ctx.saved_tensors
+        if ctx.extended:
+            g_color, g_depth, g_alpha, g_feature = grad_outs[0], grad_outs[1], grad_outs[2], grad_outs[3]
+        else:
+            g_color, g_depth, g_alpha, g_feature = grad_outs[0], None, None, None
+        args = (rs, ctx.num_rendered, ctx.capacity, ctx.extended, means3D, sh, colors_precomp, opacities, scales,
+                rotations, cov3Ds_precomp, shs_language, language_feature_precomp, ctx.confidence, radii, geom,
+                binning, img, g_color, g_depth, g_alpha, g_feature)
+        if rs.debug:
+            cpu_args = _cpu_deep_copy_tuple(args[1:])
+            try:
+                grads = _backward_impl(*args)
+            except Exception as ex:
+                torch.save(cpu_args, "snapshot_bw.dump")
+                print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+                raise ex
+        else:
+            grads = _backward_impl(*args)
+        d_means3D, d_means2D, d_sh, d_colors, d_opac, d_scales, d_rots, d_cov, d_shl, d_feat = grads
+        # order of forward()'s inputs (reference order + the two SDP-GS tensors + settings + mode flag)
+        return (d_means3D, d_means2D, d_sh, d_colors, d_opac, d_scales, d_rots, d_cov, d_shl, d_feat, None, None)
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        raster_settings, shs_language=None, language_feature_precomp=None, extended=False):
+    empty = lambda t: torch.Tensor([]) if t is None else t
+    return _RasterizeGaussians.apply(means3D, means2D, empty(sh), empty(colors_precomp), opacities, empty(scales),
+                                     empty(rotations), empty(cov3Ds_precomp), empty(shs_language),
+                                     empty(language_feature_precomp), raster_settings, bool(extended))
+
+
+def mark_visible(positions, viewmatrix, projmatrix):
+    """bool[P] frustum mask (DGR/rasterize_points.cu:198-217)."""
+    positions = _f32c(positions, "positions")
+    P = 0 if positions is None else positions.shape[0]
+    present = torch.zeros((P,), dtype=torch.bool, device=viewmatrix.device)
+    if P:
+        vm, pm = _f32c(viewmatrix, "viewmatrix"), _f32c(projmatrix, "projmatrix")
+        check(lib.b200gs_mark_visible(P, positions.data_ptr(), vm.data_ptr(), pm.data_ptr(), present.data_ptr(), _stream()))
+    return present
+
+
+def launch_count():
+    return int(lib.b200gs_launch_count())

@@ -128,6 +128,8 @@ CONFIGS = {
     # small cases for parity tests / golden fixtures
     "tiny": dict(P=600, width=80, height=56, views=2, seed=7),
     "small": dict(P=4000, width=160, height=120, views=2, seed=11),
+    # camera inside the cloud: near-plane culling, huge footprints, ragged image size (not a tile multiple)
+    "inside": dict(P=3000, width=125, height=93, views=2, seed=13, radius=0.6),
 }
 
 
@@ -138,7 +140,8 @@ def make_config(name, P=None, views=None, opacity="trained") -> Scene:
     if views is not None:
         c["views"] = views
     sc = make_scene(c["P"], c["seed"], opacity=opacity)
-    sc.cameras = ring_cameras(c["views"], c["width"], c["height"], extent=sc.extent, phase=0.1 * c["seed"])
+    sc.cameras = ring_cameras(c["views"], c["width"], c["height"], extent=sc.extent, radius=c.get("radius", 4.0),
+                              phase=0.1 * c["seed"])
     return sc
 
 

@@ -1,0 +1,306 @@
+// b200gs -- C-ABI entry points, workspace layout and stage orchestration (see include/b200gs.h).
+//
+// Stage order mirrors CudaRasterizer::Rasterizer::forward/backward
+// (DGR/cuda_rasterizer/rasterizer_impl.cu:198-336, 340-434); what differs is documented in
+// binning.cu / blend.cu.  Nothing here allocates device memory or touches the legacy default
+// stream: the caller owns the three byte workspaces and passes the stream.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "common.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+	return code;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <typename T>
+void carve(char*& p, T*& out, size_t count) {
+	p = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(p), 256));
+	out = reinterpret_cast<T*>(p);
+	p += count * sizeof(T);
+}
+
+int check_stage(const b200gs_view_t* v, cudaStream_t s, const char* what) {
+	cudaError_t e = cudaGetLastError();
+	if (e == cudaSuccess && v->debug) e = cudaStreamSynchronize(s);  // CHECK_CUDA, auxiliary.h:166-173
+	if (e != cudaSuccess) return fail(B200GS_E_CUDA, "[CUDA ERROR] in stage %s: %s", what, cudaGetErrorString(e));
+	return 0;
+}
+
+}  // namespace
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+uint32_t higher_msb(uint32_t n) {
+	uint32_t msb = sizeof(n) * 4, step = msb;
+	while (step > 1) {
+		step /= 2;
+		if (n >> msb) msb += step; else msb -= step;
+	}
+	if (n >> msb) msb++;
+	return msb;
+}
+
+// geom layout: [hdr | hist | depth look-back (4 passes) | scan state] (zeroed per forward) then the arrays
+GeomState geom_from_chunk(char* base, int P) {
+	GeomState g;
+	char* p = base;
+	const size_t n = (size_t)(P > 0 ? P : 1);
+	carve(p, g.hdr, 1);
+	carve(p, g.hist, 8 * 256);
+	carve(p, g.lookback, (size_t)4 * sort_tiles_for(P) * 256);
+	carve(p, g.scan_state, (size_t)scan_tiles_for(P) + 1);
+	carve(p, g.depths, n);
+	carve(p, g.rect, n);
+	carve(p, g.rec, 4 * n);
+	carve(p, g.clamped, n);
+	carve(p, g.order, n);
+	carve(p, g.offsets, n);
+	carve(p, g.key_a, n);
+	carve(p, g.key_b, n);
+	carve(p, g.val_b, n);
+	g.bytes = (size_t)(p - base) + 256;
+	return g;
+}
+
+static size_t geom_zero_len(int P) {
+	GeomState g = geom_from_chunk(nullptr, P);
+	return align_up(reinterpret_cast<size_t>(g.scan_state) + sizeof(unsigned long long) * ((size_t)scan_tiles_for(P) + 1), 256);
+}
+
+ImageState image_from_chunk(char* base, int W, int H) {
+	ImageState s;
+	char* p = base;
+	const size_t N = (size_t)W * H, tiles = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
+	carve(p, s.ranges, tiles ? tiles : 1);
+	carve(p, s.final_T, N ? N : 1);
+	carve(p, s.n_contrib, N ? N : 1);
+	s.bytes = (size_t)(p - base) + 256;
+	return s;
+}
+
+BinningState binning_from_chunk(char* base, int W, int H, int64_t capacity) {
+	BinningState b;
+	char* p = base;
+	const size_t n = (size_t)(capacity > 0 ? capacity : 1);
+	(void)W; (void)H;
+	carve(p, b.lookback, (size_t)4 * sort_tiles_for(capacity) * 256);  // up to 4 tile passes (bit <= 32)
+	carve(p, b.key_a, n);
+	carve(p, b.key_b, n);
+	carve(p, b.val_a, n);
+	carve(p, b.val_b, n);
+	b.sorted_keys = b.key_a;
+	b.sorted_vals = b.val_a;
+	b.bytes = (size_t)(p - base) + 256;
+	return b;
+}
+
+static size_t binning_zero_len(int64_t capacity) {
+	BinningState b = binning_from_chunk(nullptr, 0, 0, capacity);
+	return reinterpret_cast<size_t>(b.key_a);
+}
+
+static void resolve_sorted(const b200gs_view_t* v, BinningState& bs) {
+	const uint32_t gx = (v->width + TILE_X - 1) / TILE_X, gy = (v->height + TILE_Y - 1) / TILE_Y;
+	const int passes = ((int)higher_msb(gx * gy) + 7) / 8;
+	bs.sorted_keys = (passes & 1) ? bs.key_b : bs.key_a;
+	bs.sorted_vals = (passes & 1) ? bs.val_b : bs.val_a;
+}
+
+static int validate(const b200gs_view_t* v, const b200gs_gaussians_t* g, const b200gs_workspace_t* ws) {
+	if (!v || !g || !ws) return fail(B200GS_E_ARG, "null argument");
+	if (g->P < 0 || v->width <= 0 || v->height <= 0) return fail(B200GS_E_ARG, "bad sizes P=%d W=%d H=%d", g->P, v->width, v->height);
+	if (((v->width + TILE_X - 1) / TILE_X) > 65535 || ((v->height + TILE_Y - 1) / TILE_Y) > 65535)
+		return fail(B200GS_E_ARG, "image too large for 16-bit tile rects");
+	if (g->P > 0) {
+		if (!g->means3D || !g->opacities) return fail(B200GS_E_ARG, "means3D and opacities are required");
+		if ((g->shs == nullptr) == (g->colors_precomp == nullptr))
+			return fail(B200GS_E_ARG, "Please provide excatly one of either SHs or precomputed colors!");
+		const bool sr = g->scales != nullptr && g->rotations != nullptr;
+		if (sr == (g->cov3D_precomp != nullptr) || ((g->scales != nullptr) != (g->rotations != nullptr)))
+			return fail(B200GS_E_ARG, "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+		if (g->shs && v->sh_coeffs < (v->sh_degree + 1) * (v->sh_degree + 1))
+			return fail(B200GS_E_ARG, "sh_coeffs=%d too small for sh_degree=%d", v->sh_coeffs, v->sh_degree);
+		if (v->sh_degree < 0 || v->sh_degree > 3) return fail(B200GS_E_ARG, "sh_degree must be 0..3");
+	}
+	if (!v->background || !v->viewmatrix || !v->projmatrix || !v->campos) return fail(B200GS_E_ARG, "view pointers are required");
+	if (!ws->geom || ws->geom_bytes < b200gs_geom_bytes(g->P)) return fail(B200GS_E_ARG, "geom workspace too small");
+	if (!ws->image || ws->image_bytes < b200gs_image_bytes(v->width, v->height)) return fail(B200GS_E_ARG, "image workspace too small");
+	return 0;
+}
+
+extern "C" {
+
+int b200gs_version(void) { return B200GS_VERSION; }
+const char* b200gs_last_error(void) { return g_err; }
+int64_t b200gs_launch_count(void) { return g_launches.load(); }
+void b200gs_abi_sizes(int64_t* out6) {
+	out6[0] = sizeof(b200gs_view_t); out6[1] = sizeof(b200gs_gaussians_t); out6[2] = sizeof(b200gs_outputs_t);
+	out6[3] = sizeof(b200gs_workspace_t); out6[4] = sizeof(b200gs_grad_outputs_t); out6[5] = sizeof(b200gs_grads_t);
+}
+
+size_t b200gs_geom_bytes(int32_t P) { return geom_from_chunk(nullptr, P).bytes; }
+size_t b200gs_image_bytes(int32_t width, int32_t height) { return image_from_chunk(nullptr, width, height).bytes; }
+size_t b200gs_binning_bytes(int64_t capacity) { return binning_from_chunk(nullptr, 0, 0, capacity).bytes; }
+size_t b200gs_scratch_bytes(int32_t P) { return (size_t)(P > 0 ? P : 1) * GREC_FLOATS * sizeof(float); }
+
+void b200gs_geom_layout(int32_t P, int64_t* off) {
+	GeomState g = geom_from_chunk(nullptr, P);
+	off[0] = (int64_t)reinterpret_cast<size_t>(g.hdr);
+	off[1] = (int64_t)reinterpret_cast<size_t>(g.depths);
+	off[2] = (int64_t)reinterpret_cast<size_t>(g.rect);
+	off[3] = (int64_t)reinterpret_cast<size_t>(g.rec);
+	off[4] = (int64_t)reinterpret_cast<size_t>(g.clamped);
+	off[5] = (int64_t)reinterpret_cast<size_t>(g.order);
+	off[6] = (int64_t)reinterpret_cast<size_t>(g.offsets);
+}
+void b200gs_image_layout(int32_t width, int32_t height, int64_t* off) {
+	ImageState s = image_from_chunk(nullptr, width, height);
+	off[0] = (int64_t)reinterpret_cast<size_t>(s.final_T);
+	off[1] = (int64_t)reinterpret_cast<size_t>(s.n_contrib);
+	off[2] = (int64_t)reinterpret_cast<size_t>(s.ranges);
+}
+void b200gs_binning_layout(int32_t width, int32_t height, int64_t capacity, int64_t* off) {
+	BinningState b = binning_from_chunk(nullptr, width, height, capacity);
+	b200gs_view_t v;
+	memset(&v, 0, sizeof(v));
+	v.width = width; v.height = height;
+	resolve_sorted(&v, b);
+	off[0] = (int64_t)reinterpret_cast<size_t>(b.sorted_vals);
+	off[1] = (int64_t)reinterpret_cast<size_t>(b.sorted_keys);
+}
+
+int b200gs_forward_preprocess(const b200gs_view_t* v, const b200gs_gaussians_t* g, const b200gs_outputs_t* out,
+                              const b200gs_workspace_t* ws, void* stream_, int64_t* num_rendered_host) {
+	if (int e = validate(v, g, ws)) return e;
+	if (!out || (g->P > 0 && !out->radii)) return fail(B200GS_E_ARG, "radii output is required");
+	cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+	const int P = g->P;
+	char* gbase = reinterpret_cast<char*>(ws->geom);
+	GeomState gs = geom_from_chunk(gbase, P);
+	ImageState is = image_from_chunk(reinterpret_cast<char*>(ws->image), v->width, v->height);
+	const size_t tiles = (size_t)((v->width + TILE_X - 1) / TILE_X) * ((v->height + TILE_Y - 1) / TILE_Y);
+	cudaMemsetAsync(gbase, 0, geom_zero_len(P), stream);
+	cudaMemsetAsync(is.ranges, 0, tiles * sizeof(uint2), stream);  // rasterizer_impl.cu:310
+	if (P > 0) {
+		launch_preprocess_forward(*v, *g, out->radii, gs, stream);
+		if (int e = check_stage(v, stream, "preprocess")) return e;
+		launch_depth_order(gs, P, stream);
+		if (int e = check_stage(v, stream, "depth order / scan")) return e;
+	}
+	if (num_rendered_host) {
+		unsigned long long n = 0;
+		cudaError_t e = cudaMemcpyAsync(&n, &gs.hdr->num_rendered, sizeof(n), cudaMemcpyDeviceToHost, stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+		if (e != cudaSuccess) return fail(B200GS_E_CUDA, "[CUDA ERROR] reading num_rendered: %s", cudaGetErrorString(e));
+		*num_rendered_host = (int64_t)n;
+	}
+	return 0;
+}
+
+int b200gs_forward_render(const b200gs_view_t* v, const b200gs_gaussians_t* g, const b200gs_outputs_t* out,
+                          const b200gs_workspace_t* ws, int64_t capacity, void* stream_) {
+	if (int e = validate(v, g, ws)) return e;
+	if (!out || !out->color) return fail(B200GS_E_ARG, "color output is required");
+	if (v->extended && (!out->depth || !out->alpha || !out->feature)) return fail(B200GS_E_ARG, "extended outputs are required");
+	if (capacity < 0) return fail(B200GS_E_ARG, "negative capacity");
+	if (capacity > 0xFFFFFFFFll) return fail(B200GS_E_ARG, "capacity exceeds 32-bit instance offsets");
+	if (!ws->binning || ws->binning_bytes < b200gs_binning_bytes(capacity)) return fail(B200GS_E_ARG, "binning workspace too small");
+	cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+	const int P = g->P;
+	GeomState gs = geom_from_chunk(reinterpret_cast<char*>(ws->geom), P);
+	ImageState is = image_from_chunk(reinterpret_cast<char*>(ws->image), v->width, v->height);
+	BinningState bs = binning_from_chunk(reinterpret_cast<char*>(ws->binning), v->width, v->height, capacity);
+	resolve_sorted(v, bs);
+	if (P > 0 && capacity > 0) {
+		cudaMemsetAsync(ws->binning, 0, binning_zero_len(capacity), stream);
+		launch_emit(*v, gs, bs, P, capacity, stream);
+		if (int e = check_stage(v, stream, "duplicate-with-keys")) return e;
+		launch_tile_sort_and_ranges(*v, gs, bs, is, capacity, stream);
+		if (int e = check_stage(v, stream, "tile sort / ranges")) return e;
+	}
+	launch_blend_forward(*v, gs, bs, is, *out, stream);
+	return check_stage(v, stream, "blend forward");
+}
+
+int b200gs_forward(const b200gs_view_t* v, const b200gs_gaussians_t* g, const b200gs_outputs_t* out,
+                   const b200gs_workspace_t* ws, int64_t capacity, void* stream) {
+	if (int e = b200gs_forward_preprocess(v, g, out, ws, stream, nullptr)) return e;
+	return b200gs_forward_render(v, g, out, ws, capacity, stream);
+}
+
+int b200gs_forward_status(const b200gs_workspace_t* ws, void* stream_, int64_t* num_rendered, int32_t* overflow) {
+	if (!ws || !ws->geom) return fail(B200GS_E_ARG, "null workspace");
+	cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+	GeomHeader h;
+	cudaError_t e = cudaMemcpyAsync(&h, ws->geom, sizeof(h), cudaMemcpyDeviceToHost, stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+	if (e != cudaSuccess) return fail(B200GS_E_CUDA, "[CUDA ERROR] reading status: %s", cudaGetErrorString(e));
+	if (num_rendered) *num_rendered = (int64_t)h.num_rendered;
+	if (overflow) *overflow = (int32_t)h.overflow;
+	if (h.overflow & 2u) return fail(B200GS_E_ARG, "Point is filtered although prefiltered is set. This shouldn't happen!");
+	if (h.overflow & 1u) return fail(B200GS_E_OVERFLOW, "num_rendered=%lld exceeds the binning capacity", (long long)h.num_rendered);
+	return 0;
+}
+
+int b200gs_backward(const b200gs_view_t* v, const b200gs_gaussians_t* g, const int32_t* radii,
+                    const b200gs_workspace_t* ws, int64_t capacity, const b200gs_grad_outputs_t* gout,
+                    const b200gs_grads_t* grads, void* stream_) {
+	if (int e = validate(v, g, ws)) return e;
+	if (!gout || !grads) return fail(B200GS_E_ARG, "null gradient structs");
+	const int P = g->P;
+	if (P == 0) return 0;  // rasterize_points.cu:161
+	if (!radii || !grads->scratch) return fail(B200GS_E_ARG, "radii and scratch are required");
+	if (!ws->binning || ws->binning_bytes < b200gs_binning_bytes(capacity)) return fail(B200GS_E_ARG, "binning workspace too small");
+	cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+	GeomState gs = geom_from_chunk(reinterpret_cast<char*>(ws->geom), P);
+	ImageState is = image_from_chunk(reinterpret_cast<char*>(ws->image), v->width, v->height);
+	BinningState bs = binning_from_chunk(reinterpret_cast<char*>(ws->binning), v->width, v->height, capacity);
+	resolve_sorted(v, bs);
+	float* grec = reinterpret_cast<float*>(grads->scratch);
+	cudaMemsetAsync(grec, 0, b200gs_scratch_bytes(P), stream);
+	launch_blend_backward(*v, gs, bs, is, *gout, grec, stream);
+	if (int e = check_stage(v, stream, "blend backward")) return e;
+	launch_preprocess_backward(*v, *g, radii, gs, grec, *grads, stream);
+	return check_stage(v, stream, "preprocess backward");
+}
+
+int b200gs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                        uint8_t* present, void* stream_) {
+	(void)projmatrix;  // the reference computes p_proj but its frustum test only uses p_view.z (auxiliary.h:154)
+	if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) return fail(B200GS_E_ARG, "bad arguments");
+	if (P == 0) return 0;
+	cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+	launch_mark_visible(P, means3D, viewmatrix, present, stream);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return fail(B200GS_E_CUDA, "[CUDA ERROR] mark_visible: %s", cudaGetErrorString(e));
+	return 0;
+}
+
+int b200gs_debug_sorted_keys(const b200gs_view_t* v, int32_t P, const b200gs_workspace_t* ws, int64_t capacity,
+                             uint64_t* keys_out, int64_t L, void* stream_) {
+	if (!v || !ws || !keys_out || !ws->geom || !ws->binning) return fail(B200GS_E_ARG, "null argument");
+	if (L > capacity) return fail(B200GS_E_ARG, "L exceeds capacity");
+	cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+	GeomState gs = geom_from_chunk(reinterpret_cast<char*>(ws->geom), P);
+	BinningState bs = binning_from_chunk(reinterpret_cast<char*>(ws->binning), v->width, v->height, capacity);
+	resolve_sorted(v, bs);
+	launch_debug_keys(*v, gs, bs, keys_out, L, stream);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return fail(B200GS_E_CUDA, "[CUDA ERROR] debug keys: %s", cudaGetErrorString(e));
+	return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+// b200gs -- shared declarations for the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/b200gs.h"
+
+#define TILE_X 16  // tile geometry of the reference (DGR/cuda_rasterizer/config.h:16-17); part of the
+#define TILE_Y 16  // bit-exact contract (tile rects, sort keys, tile ranges)
+#define TILE_PIX (TILE_X * TILE_Y)
+
+// Per-Gaussian "splat record": everything the blend kernels need, packed into 64 bytes so that a
+// tile's gather touches exactly two fully-used 32-B sectors per Gaussian.
+//   g0 = {x, y, conic.a, conic.b}
+//   g1 = {conic.c, opacity, cull_thr (= 2 ln(255 o)), -b/c}
+//   g2 = {-b/a, r, g, b}
+//   g3 = {z_view, f0, f1, f2}
+#define REC_FLOATS 16
+// Per-Gaussian gradient record accumulated by the blend backward (64 bytes):
+//   {dmean2D.x, dmean2D.y, dconic.a, dconic.b | dconic.c, dopacity, dr, dg | db, dz, df0, df1 | df2, -, -, -}
+#define GREC_FLOATS 16
+
+struct GeomHeader {  // first 256 bytes of the geom workspace
+	unsigned long long num_rendered;  // inclusive-scan total of tiles touched
+	unsigned int overflow;            // set when num_rendered > binning capacity
+	unsigned int scan_ticket;         // dynamic tile id allocator for the look-back scan
+	unsigned int sort_ticket[8];      // one per radix pass (4 depth passes + up to 4 tile passes)
+	unsigned int pad[52];
+};
+static_assert(sizeof(GeomHeader) == 256, "header size");
+
+struct GeomState {
+	GeomHeader* hdr;
+	float* depths;           // f32[P]
+	ushort4* rect;           // (x0,y0,x1,y1) tile rect per Gaussian; all-zero when culled
+	float4* rec;             // [P][4] float4 records
+	uint8_t* clamped;        // u8[P]
+	uint32_t* order;         // u32[P]  depth-sorted Gaussian ids (final sort output)
+	uint32_t* offsets;       // u32[P]  inclusive scan of tiles touched in `order` order
+	uint32_t* key_a;         // depth-sort ping-pong
+	uint32_t* key_b;
+	uint32_t* val_b;         // (val_a aliases `order`)
+	uint32_t* hist;          // [8][256] global digit histograms (4 depth passes, up to 4 tile passes)
+	uint32_t* lookback;      // [tiles_P][256] onesweep look-back words, reused by every depth pass
+	unsigned long long* scan_state;  // [scan_tiles] look-back words of the offsets scan
+	size_t bytes;
+};
+
+struct ImageState {
+	float* final_T;       // f32[N]
+	uint32_t* n_contrib;  // u32[N]
+	uint2* ranges;        // [tiles]
+	size_t bytes;
+};
+
+struct BinningState {
+	uint32_t* key_a;  // tile ids, ping
+	uint32_t* key_b;  // pong
+	uint32_t* val_a;  // Gaussian ids, ping
+	uint32_t* val_b;  // pong
+	uint32_t* lookback;  // [tiles_L][256]
+	uint32_t* sorted_vals;  // == point_list after the tile sort (val_a or val_b depending on pass parity)
+	uint32_t* sorted_keys;
+	size_t bytes;
+};
+
+// Radix sort tiling: 256 threads x ITEMS items per CTA tile.
+#define SORT_THREADS 256
+#define SORT_ITEMS_SMALL 4
+#define SORT_ITEMS_LARGE 16
+static inline int sort_items_for(int64_t n) { return n <= (1 << 20) ? SORT_ITEMS_SMALL : SORT_ITEMS_LARGE; }
+static inline int64_t sort_tiles_for(int64_t n) {
+	int64_t per = (int64_t)SORT_THREADS * sort_items_for(n);
+	return (n + per - 1) / per;
+}
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+static inline int64_t scan_tiles_for(int64_t n) { return (n + SCAN_THREADS * SCAN_ITEMS - 1) / (SCAN_THREADS * SCAN_ITEMS); }
+
+GeomState geom_from_chunk(char* base, int P);
+ImageState image_from_chunk(char* base, int W, int H);
+BinningState binning_from_chunk(char* base, int W, int H, int64_t capacity);
+uint32_t higher_msb(uint32_t n);  // getHigherMsb, DGR/cuda_rasterizer/rasterizer_impl.cu:35-50
+
+void count_launch(int n = 1);
+
+// ---- stage launchers (each enqueues on `stream`) ----
+void launch_preprocess_forward(const b200gs_view_t& v, const b200gs_gaussians_t& g, int32_t* radii, GeomState& gs,
+                               cudaStream_t stream);
+void launch_preprocess_backward(const b200gs_view_t& v, const b200gs_gaussians_t& g, const int32_t* radii,
+                                GeomState& gs, const float* grec, const b200gs_grads_t& gr, cudaStream_t stream);
+void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t stream);
+
+// stable LSD radix sort of (u32 key, u32 value) pairs on key bits [0, end_bit); n is read from
+// *n_dev (clamped to n_max) when n_dev != nullptr, else n = n_max.  Returns which buffer pair
+// holds the result (0: a, 1: b).
+int launch_radix_sort(uint32_t* key_a, uint32_t* key_b, uint32_t* val_a, uint32_t* val_b, int64_t n_max,
+                      const unsigned long long* n_dev, int end_bit, uint32_t* hist /*[passes][256]*/,
+                      uint32_t* lookback, unsigned int* tickets, cudaStream_t stream);
+void launch_depth_order(GeomState& gs, int P, cudaStream_t stream);                     // depth sort + offsets scan
+void launch_emit(const b200gs_view_t& v, GeomState& gs, BinningState& bs, int P, int64_t capacity, cudaStream_t stream);
+void launch_tile_sort_and_ranges(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
+                                 int64_t capacity, cudaStream_t stream);
+void launch_debug_keys(const b200gs_view_t& v, GeomState& gs, BinningState& bs, uint64_t* keys_out, int64_t L,
+                       cudaStream_t stream);
+
+void launch_blend_forward(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
+                          const b200gs_outputs_t& out, cudaStream_t stream);
+void launch_blend_backward(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
+                           const b200gs_grad_outputs_t& gout, float* grec, cudaStream_t stream);
+
+// ---- device helpers ----
+#ifdef __CUDACC__
+// a0*b0 + a1*b1 + a2*b2 with the rounding sequence the reference's sm_100a build executes
+// (FMUL, FFMA, FFMA); pinned with .rn intrinsics so neither cicc nor ptxas may re-associate.
+__device__ __forceinline__ float dot3_pinned(float a0, float b0, float a1, float b1, float a2, float b2) {
+	return __fmaf_rn(a2, b2, __fmaf_rn(a0, b0, __fmul_rn(a1, b1)));
+}
+// row r of transformPoint4x3/4x4 (DGR/cuda_rasterizer/auxiliary.h:58-77)
+__device__ __forceinline__ float xform_row(const float* __restrict__ m, int r, float x, float y, float z) {
+	return __fadd_rn(dot3_pinned(x, m[r], y, m[4 + r], z, m[8 + r]), m[12 + r]);
+}
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
+#endif
