@@ -71,7 +71,7 @@ GeomState geom_from_chunk(char* base, int P) {
 	carve(p, g.key_a, n);
 	carve(p, g.key_b, n);
 	carve(p, g.val_b, n);
-	g.bytes = (size_t)(p - base) + 256;
+	g.bytes = align_up((size_t)(p - base), 256) + 256;
 	return g;
 }
 
@@ -87,7 +87,7 @@ ImageState image_from_chunk(char* base, int W, int H) {
 	carve(p, s.ranges, tiles ? tiles : 1);
 	carve(p, s.final_T, N ? N : 1);
 	carve(p, s.n_contrib, N ? N : 1);
-	s.bytes = (size_t)(p - base) + 256;
+	s.bytes = align_up((size_t)(p - base), 256) + 256;
 	return s;
 }
 
@@ -103,7 +103,7 @@ BinningState binning_from_chunk(char* base, int W, int H, int64_t capacity) {
 	carve(p, b.val_b, n);
 	b.sorted_keys = b.key_a;
 	b.sorted_vals = b.val_a;
-	b.bytes = (size_t)(p - base) + 256;
+	b.bytes = align_up((size_t)(p - base), 256) + 256;
 	return b;
 }
 
