@@ -1,0 +1,528 @@
+#!/usr/bin/env python
+"""bench.py -- rasterizer forward+backward throughput on the BASELINE.json workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200gs|reference] [--workload NAME] [--mode extended|vanilla]
+
+A "step" is one rasterizer forward+backward of one view of the named synthetic workload (default: the
+LLFF fern shape of BASELINE.json configs[0]/[1]: 100k Gaussians, 504x378, SH degree 3, the SDP-GS output
+set color+depth+alpha+feature; one view per step, cycling through the 3 training views).  At N>1 every
+rank processes its own view per step (image-parallel training, weak scaling) and the per-Gaussian
+gradients are combined with one NCCL all-reduce inside the step.
+
+One JSON line on stdout (rank 0):
+  value / ms_per_step : whole-job views/s and ms per step with inputs resident in HBM (CUDA events around a
+                        CUDA-graph replay of the step on the launch stream; L2 flushed between steps);
+  e2e                 : the same through the public drop-in API (GaussianRasterizer + autograd) with the
+                        Gaussian parameters copied from pinned HOST memory every step and the loss read back;
+  roofline            : dominant kernel, algorithmic bytes / CUDA-event duration;
+  cpu_baseline        : the CPU oracle port (oracle/gs_oracle.c, OpenMP) on one view of the same workload.
+`--impl reference` times the UNMODIFIED reference CUDA rasterizer (oracle/_ref, built from /root/reference)
+on the same workload; the SDP-GS outputs are obtained the only way its 3-channel kernel can deliver them, by
+channel packing (3 forward+backward calls: rgb | z,1,f0 | f1,f2,0); the single-call vanilla comparison is
+reported in `vanilla` on both arms.  If oracle/_ref is missing the arm falls back to the CPU oracle port.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "sdp-gs_b200"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from b200gs import synthetic as syn  # noqa: E402
+from b200gs.bytes_model import stage_bytes  # noqa: E402
+
+STAGES = ["memset", "preprocess", "depth_sort", "scan", "duplicate", "tile_sort", "ranges", "blend_fwd", "blend_bwd",
+          "preprocess_bwd"]
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200gs", choices=["b200gs", "reference"])
+    ap.add_argument("--workload", default="llff_fern_3view")
+    ap.add_argument("--mode", default="extended", choices=["extended", "vanilla"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--P", type=int, default=None, help="override the Gaussian count of the workload")
+    return ap.parse_args()
+
+
+def dist_init(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(local)
+    return rank, world, local
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons, smax = [], set(), None
+        for r in rows:
+            try:
+                sm.append(float(r[1])); smax = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if sm:
+            # "under load": samples in the upper half of what was seen
+            hi = [x for x in sm if x >= 0.5 * max(sm)]
+            out = dict(sm_mhz=float(np.median(hi)), sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class Workload:
+    def __init__(self, name, mode, dev, P=None):
+        self.name, self.mode, self.dev = name, mode, dev
+        cfg = syn.CONFIGS[name]
+        sc = syn.make_config(name, P=P, views=min(cfg["views"], 8))
+        self.scene = sc
+        self.extended = mode == "extended"
+        self.W, self.H = cfg["width"], cfg["height"]
+        self.host = dict(means3D=sc.means3D, shs=sc.shs, opacities=sc.opacities, scales=sc.scales, rotations=sc.rotations)
+        if self.extended:
+            self.host["features"] = sc.features
+        self.pinned = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in self.host.items()}
+        self.devt = {k: v.to(dev) for k, v in self.pinned.items()}
+        self.h2d_bytes = int(sum(v.numel() * 4 for v in self.pinned.values()))
+        self.cams = sc.cameras
+        self.bg = torch.zeros(3, device=dev)
+        self.cot = []
+        for i, cam in enumerate(self.cams):
+            self.cot.append(tuple(torch.from_numpy(c).to(dev) for c in syn.cotangents(cam, 100 + i)))
+
+    def settings(self, cam, P):
+        from diff_gaussian_rasterization import GaussianRasterizationSettings as S
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.dev)
+        kw = dict(image_height=cam.height, image_width=cam.width, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=self.bg,
+                  scale_modifier=1.0, viewmatrix=t(cam.viewmatrix), projmatrix=t(cam.projmatrix), sh_degree=3,
+                  campos=t(cam.campos), prefiltered=False, debug=False)
+        if self.extended:
+            kw.update(include_feature=True, confidence=torch.ones((P, 1), device=self.dev))
+        return S(**kw)
+
+
+def event_loop(K, warmup, step_fn, flush, world, after=None):
+    """warmup untimed steps, then K steps each bracketed by CUDA events on the current stream with an L2
+    flush between steps.  Returns (sum of step ms maxed over ranks, wall seconds of the bracket)."""
+    for i in range(warmup):
+        flush()
+        step_fn(i)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(K):
+        flush()
+        evs[i][0].record()
+        step_fn(warmup + i)
+        evs[i][1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - t0
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, wall
+
+
+def wall_loop(K, warmup, step_fn, world):
+    for i in range(warmup):
+        step_fn(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(K):
+        step_fn(warmup + i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sec = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([sec], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+    return sec
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_b200gs(args, rank, world, local):
+    from b200gs import _lib, parallel
+    from b200gs import rasterizer as rz
+    from diff_gaussian_rasterization import GaussianRasterizer
+    dev = torch.device("cuda", local)
+    wl = Workload(args.workload, args.mode, dev, args.P)
+    P = wl.scene.P
+    ext = wl.extended
+    nviews = len(wl.cams)
+    flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    flush = lambda: flush_buf.zero_()
+
+    # instance counts per view (one synchronous forward each) -> capacity of the no-sync path
+    Ls, Vs = [], []
+    for cam in wl.cams:
+        rs = wl.settings(cam, P)
+        res = rz._forward_impl(rs, wl.devt["means3D"], wl.devt["shs"], None, wl.devt["opacities"], wl.devt["scales"],
+                               wl.devt["rotations"], None, None, wl.devt.get("features"), getattr(rs, "confidence", None), ext)
+        Ls.append(res[0]); Vs.append(int((res[6] > 0).sum().item()))
+    capacity = int(max(Ls) * 1.25) + 1024
+
+    # ---- device-resident loop: one captured CUDA graph per view, rank r starts at view r
+    bucket = parallel.FusedGradBuffer(P, dev)
+    grads_out = dict(means3D=bucket.segment("xyz"), shs=bucket.segment("shs"), opacities=bucket.segment("opacity"),
+                     scales=bucket.segment("scaling"), rotations=bucket.segment("rotation"))
+    if ext:
+        grads_out["features"] = bucket.segment("language_feature")
+    sessions = []
+    for vi, cam in enumerate(wl.cams):
+        s = rz.RasterSession(wl.settings(cam, P), means3D=wl.devt["means3D"], opacities=wl.devt["opacities"], shs=wl.devt["shs"],
+                             scales=wl.devt["scales"], rotations=wl.devt["rotations"],
+                             language_feature_precomp=wl.devt.get("features"), extended=ext, capacity=capacity,
+                             grads_out=grads_out)
+        s.cot["color"].copy_(wl.cot[vi][0])
+        if ext:
+            s.cot["depth"].copy_(wl.cot[vi][1]); s.cot["alpha"].copy_(wl.cot[vi][2]); s.cot["feature"].copy_(wl.cot[vi][3])
+        s.capture()
+        sessions.append(s)
+
+    def step_resident(i):
+        sessions[(i + rank) % nviews].replay()
+        if world > 1:
+            bucket.all_reduce()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = rz.launch_count()
+    ms_total, wall = event_loop(args.steps, args.warmup, step_resident, flush, world)
+    clocks = sampler.stop() if rank == 0 else {}
+    for s in sessions:
+        n, ov = s.status()
+        assert ov == 0, "binning capacity overflow in the timed loop"
+    # kernels launched per replayed step == kernels launched by one eager step
+    l0 = rz.launch_count()
+    sessions[0].step()
+    torch.cuda.synchronize()
+    launches_per_step = rz.launch_count() - l0
+    ms_per_step = ms_total / args.steps
+    value = world * 1000.0 / ms_per_step
+
+    # ---- per-stage timing (eager launches, CUDA events between stages on the launch stream)
+    _lib.lib.b200gs_profile_enable(1)
+    nprof = max(5, min(args.steps, 20))
+    for i in range(nprof + 2):
+        if i == 2:
+            _lib.lib.b200gs_profile_read(None, None, 1)
+        flush()
+        sessions[(i + rank) % nviews].step()
+    ms = (C.c_double * 10)(); cnt = (C.c_int64 * 10)()
+    _lib.lib.b200gs_profile_read(ms, cnt, 1)
+    _lib.lib.b200gs_profile_enable(0)
+    stage_ms = {STAGES[i]: (ms[i] / nprof) for i in range(10)}
+
+    # ---- end to end through the public API with host buffers
+    def step_e2e(i):
+        vi = (i + rank) % nviews
+        t = {k: v.to(dev, non_blocking=True).requires_grad_(True) for k, v in wl.pinned.items()}
+        rs = wl.settings_cache[vi]
+        means2D = torch.zeros((P, 3), device=dev, requires_grad=True)
+        kw = dict(means3D=t["means3D"], means2D=means2D, opacities=t["opacities"], shs=t["shs"], scales=t["scales"],
+                  rotations=t["rotations"])
+        if ext:
+            kw["language_feature_precomp"] = t["features"]
+        outs = GaussianRasterizer(rs)(**kw)
+        cot = wl.cot[vi]
+        if ext:
+            loss = (outs[0] * cot[0]).sum() + (outs[1] * cot[1]).sum() + (outs[2] * cot[2]).sum() + (outs[3] * cot[3]).sum()
+        else:
+            loss = (outs[0] * cot[0]).sum()
+        loss.backward()
+        if world > 1:
+            g = torch.cat([t[k].grad.reshape(-1) for k in sorted(t)])
+            dist.all_reduce(g)
+        return float(loss.item())
+
+    wl.settings_cache = [wl.settings(cam, P) for cam in wl.cams]
+    e2e_sec = wall_loop(args.steps, max(3, args.warmup), step_e2e, world)
+    e2e_value = world * args.steps / e2e_sec
+
+    # ---- vanilla single-call comparison point (colour only), device resident
+    vanilla = None
+    if ext and world == 1:
+        wv = Workload(args.workload, "vanilla", dev, args.P)
+        sv = []
+        for vi, cam in enumerate(wv.cams):
+            s = rz.RasterSession(wv.settings(cam, P), means3D=wv.devt["means3D"], opacities=wv.devt["opacities"], shs=wv.devt["shs"],
+                                 scales=wv.devt["scales"], rotations=wv.devt["rotations"], extended=False, capacity=capacity)
+            s.cot["color"].copy_(wv.cot[vi][0])
+            sv.append(s.capture())
+        vms, _ = event_loop(args.steps, args.warmup, lambda i: sv[i % nviews].replay(), flush, 1)
+        vanilla = dict(ms_per_view=vms / args.steps, views_per_s=1000.0 * args.steps / vms)
+
+    # ---- roofline of the dominant kernel + whole step
+    L, V = int(np.mean(Ls)), int(np.mean(Vs))
+    model = stage_bytes(P, V, L, wl.W, wl.H, sh_degree=3, sh_coeffs=16, use_sh=True, extended=ext, training=True)
+    peak, peak_src = peaks()
+    by_stage = {"preprocess": model["forward"]["preprocess"], "depth_sort": 0, "scan": model["forward"]["scan"],
+                "duplicate": model["forward"]["duplicate"], "tile_sort": model["forward"]["sort"],
+                "ranges": model["forward"]["ranges"], "blend_fwd": model["forward"]["blend_fwd"],
+                "blend_bwd": model["backward"]["blend_bwd"], "preprocess_bwd": model["backward"]["preprocess_bwd"]}
+    # the reference's single 64-bit sort is split here into depth_sort + tile_sort: charge its bytes to their sum
+    sort_ms = stage_ms["depth_sort"] + stage_ms["tile_sort"]
+    dom = max((k for k in by_stage if k not in ("depth_sort",)), key=lambda k: stage_ms[k] if k != "tile_sort" else sort_ms)
+    dom_ms = sort_ms if dom == "tile_sort" else stage_ms[dom]
+    achieved = by_stage[dom] / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dom)
+        except Exception:
+            traffic = None
+    total_bytes = model["bytes_fwd"] + model["bytes_bwd"]
+    roofline = dict(bound="hbm", kernel=dom, achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
+                    peak_source=peak_src, algorithmic_bytes=by_stage[dom], kernel_ms=dom_ms,
+                    step=dict(algorithmic_bytes=total_bytes, achieved=total_bytes / (ms_per_step * 1e-3) / 1e9,
+                              frac=total_bytes / (ms_per_step * 1e-3) / 1e9 / peak),
+                    stage_ms=stage_ms, stage_sum_ms=sum(stage_ms.values()),
+                    note="blend stages are FP32/SFU bound (256*L pair evaluations), not HBM bound; see DESIGN.md")
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(wl, 0)
+
+    if rank == 0:
+        line = dict(metric="rasterizer fwd+bwd views/s (1000/ms_per_step = ms/view; one view per train iteration)",
+                    value=value, unit="views/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step,
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload=f"{args.workload}: P={P} Gaussians, {wl.W}x{wl.H}, SH degree 3 in-kernel, "
+                                         f"outputs={'color+depth+alpha+feature' if ext else 'color'}, one view fwd+bwd per step"
+                                         + (", per-Gaussian gradient NCCL all-reduce (image-parallel)" if world > 1 else ""),
+                                P=P, width=wl.W, height=wl.H, mode=args.mode, num_rendered=L, visible=V, tiles=model["tiles"],
+                                sort_passes_model=model["passes"], l2="flushed between steps (256 MiB write)",
+                                binning="capacity mode, CUDA graph replay", parallelism=f"image-parallel x{world}"),
+                    e2e=dict(value=e2e_value, unit="views/s", ms_per_step=1000.0 * e2e_sec / args.steps,
+                             h2d_bytes_per_step=wl.h2d_bytes, d2h_bytes_per_step=12,
+                             path="diff_gaussian_rasterization.GaussianRasterizer (autograd), pinned host -> device per step, loss.item()"),
+                    gpu_launches=int(launches_per_step * args.steps), gpu_launches_per_step=int(launches_per_step),
+                    clocks=clocks, roofline=roofline, cpu_baseline=cpu, vanilla=vanilla, impl="b200gs",
+                    wall_s=wall)
+        print(json.dumps(line))
+
+
+def cpu_baseline(wl, vi):
+    """The CPU oracle port on one view (forward + backward), all host threads."""
+    from oracle import cpu_oracle as orc
+    sc, cam = wl.scene, wl.cams[vi]
+    cot = [c.cpu().numpy() for c in wl.cot[vi]]
+    t0 = time.perf_counter()
+    o = orc.forward(sc.means3D, sc.opacities, cam, np.zeros(3, np.float32), shs=sc.shs, scales=sc.scales,
+                    rotations=sc.rotations, extended=wl.extended, features=sc.features if wl.extended else None)
+    orc.backward(o, *(cot if wl.extended else cot[:1]))
+    sec = time.perf_counter() - t0
+    return dict(value=1.0 / sec, unit="views/s", ms_per_view=1000.0 * sec, cores=orc.num_threads(), kind="port",
+                sample="1 view forward+backward of the same workload (oracle/gs_oracle.c, OpenMP)")
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+class RefBench:
+    """Pre-allocated driver of the unmodified reference kernels (oracle/_ref) for timing."""
+
+    def __init__(self, wl, binning_bytes):
+        from oracle import ref_cuda
+        self.L = ref_cuda.lib()
+        self.wl = wl
+        dev = wl.dev
+        P, W, H = wl.scene.P, wl.W, wl.H
+        self.P, self.W, self.H = P, W, H
+        z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
+        self.color = z(3, H, W)
+        self.radii = torch.zeros((P,), dtype=torch.int32, device=dev)
+        self.gb, self.ib = self.L.ref_required_geom(P), self.L.ref_required_image(W * H)
+        self.geom = torch.zeros((self.gb,), dtype=torch.uint8, device=dev)
+        self.img = torch.zeros((self.ib,), dtype=torch.uint8, device=dev)
+        self.bb = binning_bytes
+        self.binning = torch.zeros((binning_bytes,), dtype=torch.uint8, device=dev)
+        self.g = dict(means2D=z(P, 3), conic=z(P, 4), opacities=z(P, 1), colors=z(P, 3), means3D=z(P, 3), cov3D=z(P, 6),
+                      shs=z(P, 16, 3), scales=z(P, 3), rotations=z(P, 4))
+        off = (C.c_int64 * 9)()
+        self.L.ref_geom_layout(C.c_void_p(0), C.c_int(P), off)
+        self.depths = self.geom[int(off[0]):int(off[0]) + 4 * P].view(torch.float32)
+        self.zero3 = z(3)
+        self.pack1, self.pack2 = z(P, 3), z(P, 3)
+        self.needed = C.c_size_t(0)
+        self.cams = []
+        for cam in wl.cams:
+            t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+            self.cams.append((cam, t(cam.viewmatrix), t(cam.projmatrix), t(cam.campos)))
+
+    def fwd_bwd(self, vi, T, shs, colors, bg, dpix, D):
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        cam, view, proj, campos = self.cams[vi]
+        P, W, H = self.P, self.W, self.H
+        M = 16 if shs is not None else 0
+        n = self.L.ref_forward(C.c_int(P), C.c_int(D), C.c_int(M), p(bg), C.c_int(W), C.c_int(H), p(T["means3D"]), p(shs), p(colors),
+                               p(T["opacities"]), p(T["scales"]), C.c_float(1.0), p(T["rotations"]), None, p(view), p(proj), p(campos),
+                               C.c_float(cam.tanfovx), C.c_float(cam.tanfovy), C.c_int(0), p(self.color), p(self.radii),
+                               p(self.geom), C.c_size_t(self.gb), p(self.binning), C.c_size_t(self.bb), C.byref(self.needed),
+                               p(self.img), C.c_size_t(self.ib), C.c_int(0))
+        if n < 0:
+            raise RuntimeError("reference forward failed: " + self.L.ref_last_error().decode())
+        for t in self.g.values():  # the nine torch::zeros of rasterize_points.cu:151-159
+            t.zero_()
+        g = self.g
+        rc = self.L.ref_backward(C.c_int(P), C.c_int(D), C.c_int(M), C.c_int(n), p(bg), C.c_int(W), C.c_int(H), p(T["means3D"]), p(shs),
+                                 p(colors), p(T["scales"]), C.c_float(1.0), p(T["rotations"]), None, p(view), p(proj), p(campos),
+                                 C.c_float(cam.tanfovx), C.c_float(cam.tanfovy), p(self.radii), p(self.geom), p(self.binning), p(self.img),
+                                 p(dpix), p(g["means2D"]), p(g["conic"]), p(g["opacities"]), p(g["colors"]), p(g["means3D"]),
+                                 p(g["cov3D"]), p(g["shs"]), p(g["scales"]), p(g["rotations"]), C.c_int(0))
+        if rc != 0:
+            raise RuntimeError("reference backward failed")
+        return n
+
+    def step(self, vi, T, extended):
+        cot = self.wl.cot[vi]
+        self.fwd_bwd(vi, T, T["shs"], None, self.wl.bg, cot[0], 3)
+        if extended:
+            f = T["features"]
+            self.pack1[:, 0] = self.depths; self.pack1[:, 1] = 1.0; self.pack1[:, 2] = f[:, 0]
+            self.pack2[:, 0] = f[:, 1]; self.pack2[:, 1] = f[:, 2]
+            self.fwd_bwd(vi, T, None, self.pack1, self.zero3, self.cot1[vi], 0)
+            self.fwd_bwd(vi, T, None, self.pack2, self.zero3, self.cot2[vi], 0)
+
+
+def run_reference(args, rank, world, local):
+    from oracle import ref_cuda
+    if rank != 0:
+        return
+    dev = torch.device("cuda", 0)
+    wl = Workload(args.workload, args.mode, dev, args.P)
+    P, ext, nviews = wl.scene.P, wl.extended, len(wl.cams)
+    if not ref_cuda.available():
+        cpu = cpu_baseline(wl, 0)
+        print(json.dumps(dict(impl="reference", metric="rasterizer fwd+bwd views/s (1000/ms_per_step = ms/view; one view per train iteration)",
+                              value=cpu["value"], unit="views/s", n_gpus=1, steps=1, warmup=0, ms_per_step=cpu["ms_per_view"],
+                              higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                              config=dict(workload=args.workload, note="oracle/_ref missing: CPU oracle port timed instead"),
+                              cpu_baseline=cpu, e2e=dict(value=cpu["value"], unit="views/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+        return
+    # size the binning buffer once with the decode path
+    s0 = ref_cuda.forward(wl.host["means3D"], wl.host["opacities"], wl.cams[0], np.zeros(3, np.float32), shs=wl.host["shs"],
+                          scales=wl.host["scales"], rotations=wl.host["rotations"], decode=False)
+    rb = RefBench(wl, int(s0.binning.numel() * 1.3))
+    del s0
+    H, W = wl.H, wl.W
+    if ext:
+        rb.cot1 = [torch.cat([c[1], c[2], c[3][0:1]], 0).contiguous() for c in wl.cot]
+        rb.cot2 = [torch.cat([c[3][1:3], torch.zeros((1, H, W), device=dev)], 0).contiguous() for c in wl.cot]
+    flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    flush = lambda: flush_buf.zero_()
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms_total, wall = event_loop(args.steps, args.warmup, lambda i: rb.step(i % nviews, wl.devt, ext), flush, 1)
+    clocks = sampler.stop()
+    ms_per_step = ms_total / args.steps
+    vanilla = None
+    if ext:
+        vms, _ = event_loop(args.steps, args.warmup, lambda i: rb.step(i % nviews, wl.devt, False), flush, 1)
+        vanilla = dict(ms_per_view=vms / args.steps, views_per_s=1000.0 * args.steps / vms)
+
+    def step_e2e(i):
+        T = {k: v.to(dev, non_blocking=True) for k, v in wl.pinned.items()}
+        rb.step(i % nviews, T, ext)
+        return float(rb.color.sum().item())
+
+    e2e_sec = wall_loop(args.steps, max(3, args.warmup), step_e2e, 1)
+    calls = 3 if ext else 1
+    print(json.dumps(dict(
+        impl="reference", metric="rasterizer fwd+bwd views/s (1000/ms_per_step = ms/view; one view per train iteration)",
+        value=1000.0 / ms_per_step, unit="views/s", n_gpus=1, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step,
+        higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+        config=dict(workload=f"{args.workload}: P={P} Gaussians, {wl.W}x{wl.H}, SH degree 3 in-kernel, "
+                             f"outputs={'color+depth+alpha+feature via 3 channel-packed calls' if ext else 'color'}",
+                    P=P, width=wl.W, height=wl.H, mode=args.mode, reference_calls_per_step=calls,
+                    l2="flushed between steps (256 MiB write)",
+                    note="unmodified reference CUDA rasterizer (diff-gaussian-rasterization) built for sm_100a, torch-free shim"),
+        e2e=dict(value=args.steps / e2e_sec, unit="views/s", ms_per_step=1000.0 * e2e_sec / args.steps,
+                 h2d_bytes_per_step=wl.h2d_bytes, d2h_bytes_per_step=4 + 4 * calls),
+        gpu_launches=0, clocks=clocks, vanilla=vanilla,
+        cpu_baseline=dict(value=None, unit="views/s", cores=0, kind="reference",
+                          sample="the reference path is CUDA-only: this arm runs its own kernels on the B200, not a CPU port"),
+        wall_s=wall)))
+
+
+def main():
+    args = parse()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    rank, world, local = dist_init(args)
+    if args.impl == "reference":
+        run_reference(args, rank, world, local)
+    else:
+        run_b200gs(args, rank, world, local)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

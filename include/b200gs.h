@@ -173,6 +173,13 @@ int b200gs_debug_sorted_keys(const b200gs_view_t* view, int32_t P, const b200gs_
                              uint64_t* keys_out, int64_t L, void* stream);
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t b200gs_launch_count(void);
+/* Optional per-stage timing with CUDA events on the launch stream (bench.py's roofline numbers).
+ * Stages: 0 memsets, 1 preprocess fwd, 2 depth sort, 3 offsets scan, 4 duplicate-with-keys, 5 tile sort,
+ * 6 tile ranges, 7 blend fwd, 8 blend bwd, 9 preprocess bwd.  profile_read synchronizes the pending events and
+ * returns accumulated milliseconds / call counts per stage (arrays of 10). */
+#define B200GS_NUM_STAGES 10
+void b200gs_profile_enable(int32_t on);
+int b200gs_profile_read(double* ms_out10, int64_t* n_out10, int32_t reset);
 /* sizeof() of the six structs above, in declaration order (lets a foreign-language binding check its layout). */
 void b200gs_abi_sizes(int64_t* out6);
 

@@ -61,7 +61,7 @@ EXPORTS = [
     "b200gs_scratch_bytes", "b200gs_forward_preprocess", "b200gs_forward_render", "b200gs_forward",
     "b200gs_forward_status", "b200gs_backward", "b200gs_mark_visible", "b200gs_geom_layout",
     "b200gs_image_layout", "b200gs_binning_layout", "b200gs_debug_sorted_keys", "b200gs_launch_count",
-    "b200gs_abi_sizes",
+    "b200gs_abi_sizes", "b200gs_profile_enable", "b200gs_profile_read",
 ]
 
 
@@ -94,6 +94,8 @@ def _load():
     lib.b200gs_binning_layout.argtypes = [C.c_int32, C.c_int32, C.c_int64, P(C.c_int64)]
     lib.b200gs_debug_sorted_keys.argtypes = [P(View), C.c_int32, P(Workspace), C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
     lib.b200gs_abi_sizes.argtypes = [P(C.c_int64)]
+    lib.b200gs_profile_enable.argtypes = [C.c_int32]
+    lib.b200gs_profile_read.argtypes = [P(C.c_double), P(C.c_int64), C.c_int32]
     sizes = (C.c_int64 * 6)()
     lib.b200gs_abi_sizes(sizes)
     mine = [C.sizeof(t) for t in (View, Gaussians, Outputs, Workspace, GradOutputs, Grads)]

@@ -1,0 +1,121 @@
+"""Multi-GPU drivers for the two ways the rasterizer path shards on one 8xB200 NVSwitch box
+(SURVEY.md §8e).  One process per GPU, `torch.distributed` for the plumbing (NCCL on GPUs; the
+same code runs under gloo on CPU for the host-logic tests).
+
+* View-sharded rendering (model: render.py:38-39): parameters replicated, rank r renders views
+  r, r+n, ...; no data-path collective.
+* Image-parallel training (train.py:93-231 with one view per rank): each rank renders and
+  back-propagates its own views; the per-Gaussian gradients of all ranks are combined with ONE
+  all-reduce over a fused buffer of P*64 f32 (62 parameter-gradient floats per Gaussian for the Adam
+  groups of scene/gaussian_model.py:228-237 -- xyz 3, f_dc 3 + f_rest 45, opacity 1, scaling 3,
+  rotation 4, language_feature 3 -- plus the two densification statistics xyz_gradient_accum and
+  denom, scene/gaussian_model.py:610-612), and max_radii2D with one MAX all-reduce, so that the Adam
+  step and densify/prune are applied identically on every rank.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+# segments of the fused buffer, floats per Gaussian
+SLOTS = (("xyz", 3), ("shs", 48), ("opacity", 1), ("scaling", 3), ("rotation", 4), ("language_feature", 3),
+         ("xyz_gradient_accum", 1), ("denom", 1))
+FUSED_WIDTH = sum(w for _, w in SLOTS)  # 64 floats = 256 B per Gaussian
+assert FUSED_WIDTH == 64
+
+
+def shard_views(n_views, rank, world_size):
+    """Indices of the views rank `rank` owns (round-robin, like `views[r::n]`)."""
+    return list(range(rank, n_views, world_size))
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+class FusedGradBuffer:
+    """One flat f32 allocation of P*64 floats holding every per-Gaussian quantity of an image-parallel
+    step as back-to-back contiguous segments ([P,3] xyz, [P,16,3] shs = f_dc + f_rest, [P,1] opacity, ...).
+    The rasterizer backward can write straight into the segments (they are ordinary contiguous tensors), so
+    combining all ranks' gradients is ONE all-reduce with no packing pass."""
+
+    def __init__(self, P, device, sh_coeffs=16):
+        assert sh_coeffs == 16, "segment table assumes max_sh_degree = 3 (arguments/__init__.py:49)"
+        self.P = P
+        self.flat = torch.zeros((P * FUSED_WIDTH,), dtype=torch.float32, device=device)
+        self.max_radii2D = torch.zeros((P,), dtype=torch.int32, device=device)
+        self.seg = {}
+        c = 0
+        for name, w in SLOTS:
+            self.seg[name] = self.flat[c * P:(c + w) * P].view(P, w)
+            c += w
+        self.seg["shs"] = self.seg["shs"].view(P, 16, 3)
+
+    def segment(self, name):
+        return self.seg[name]
+
+    def zero_(self):
+        self.flat.zero_()
+        self.max_radii2D.zero_()
+
+    def add_statistics(self, viewspace_grad, radii):
+        """Densification statistics of one rendered view (train.py:218-221, scene/gaussian_model.py:610-612)."""
+        vis = radii > 0
+        self.seg["xyz_gradient_accum"][vis] += torch.norm(viewspace_grad[vis, :2], dim=-1, keepdim=True)
+        self.seg["denom"][vis] += 1.0
+        self.max_radii2D[vis] = torch.maximum(self.max_radii2D[vis], radii[vis].to(torch.int32))
+
+    def accumulate_view(self, *, d_xyz, d_shs, d_opacity, d_scaling, d_rotation, d_feature, viewspace_grad, radii):
+        """Add one rendered view's gradients and densification statistics."""
+        self.seg["xyz"].add_(d_xyz)
+        if d_shs is not None:
+            self.seg["shs"].add_(d_shs)
+        self.seg["opacity"].add_(d_opacity.reshape(-1, 1))
+        self.seg["scaling"].add_(d_scaling)
+        self.seg["rotation"].add_(d_rotation)
+        if d_feature is not None:
+            self.seg["language_feature"].add_(d_feature)
+        self.add_statistics(viewspace_grad, radii)
+
+    def all_reduce(self, async_op=False):
+        """SUM over ranks of the fused buffer, MAX of max_radii2D."""
+        rank, n = world()
+        if n == 1:
+            return None
+        w1 = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=True)
+        w2 = dist.all_reduce(self.max_radii2D, op=dist.ReduceOp.MAX, async_op=True)
+        if async_op:
+            return (w1, w2)
+        w1.wait()
+        w2.wait()
+        return None
+
+
+def render_views_sharded(render_fn, n_views, gather=False):
+    """Each rank calls `render_fn(view_index)` for the views it owns.  Returns {index: result}; with
+    gather=True rank 0 additionally receives every rank's {index: result} (results must be picklable)."""
+    rank, n = world()
+    mine = {i: render_fn(i) for i in shard_views(n_views, rank, n)}
+    if gather and n > 1:
+        out = [None] * n if rank == 0 else None
+        dist.gather_object(mine, out, dst=0)
+        if rank == 0:
+            merged = {}
+            for d in out:
+                merged.update(d)
+            return merged
+    return mine
+
+
+def image_parallel_step(fwd_bwd_fn, view_indices, bucket):
+    """One image-parallel training step: this rank runs `fwd_bwd_fn(view_index)` (which must return the
+    kwargs of FusedGradBuffer.accumulate_view) for its share of `view_indices`, then the fused all-reduce.
+    After return `bucket` holds the same totals on every rank."""
+    rank, n = world()
+    bucket.zero_()
+    for k in shard_views(len(view_indices), rank, n):
+        bucket.accumulate_view(**fwd_bwd_fn(view_indices[k]))
+    bucket.all_reduce()
+    return bucket

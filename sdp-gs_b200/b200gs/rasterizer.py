@@ -257,3 +257,123 @@ def mark_visible(positions, viewmatrix, projmatrix):
 
 def launch_count():
     return int(lib.b200gs_launch_count())
+
+
+class RasterSession:
+    """Pre-planned forward(+backward) over fixed device buffers: no allocation, no host sync, so a whole
+    step can be captured once into a CUDA graph and replayed (`capture()` / `replay()`).
+
+    This is the steady-state path for a training loop whose P and image size do not change between
+    densification events: the binning workspace is sized for `capacity` instances; if a view ever needs
+    more, the overflow flag is raised on the device (`status()` reads it back, which synchronizes)."""
+
+    def __init__(self, raster_settings, *, means3D, opacities, shs=None, colors_precomp=None, scales=None,
+                 rotations=None, cov3D_precomp=None, shs_language=None, language_feature_precomp=None,
+                 extended=False, capacity, grads_out=None, with_backward=True):
+        rs = raster_settings
+        self.rs, self.extended, self.capacity = rs, bool(extended), int(capacity)
+        dev = means3D.device
+        self.dev = dev
+        P = self.P = means3D.shape[0]
+        H, W = int(rs.image_height), int(rs.image_width)
+        self._keep = []
+        f = lambda t, n: _f32c(t, n)
+        self.inputs = dict(means3D=f(means3D, "means3D"), opacities=f(opacities, "opacities"), shs=f(shs, "shs"),
+                           colors_precomp=f(colors_precomp, "colors_precomp"), scales=f(scales, "scales"),
+                           rotations=f(rotations, "rotations"), cov3D_precomp=f(cov3D_precomp, "cov3D_precomp"),
+                           shs_language=f(shs_language, "shs_language"),
+                           language_feature_precomp=f(language_feature_precomp, "language_feature_precomp"),
+                           confidence=f(getattr(rs, "confidence", None), "confidence"))
+        i = self.inputs
+        M = 0 if i["shs"] is None else int(i["shs"].shape[1])
+        g = self.g = Gaussians()
+        g.P = P
+        g.means3D, g.shs, g.colors_precomp, g.opacities = _ptr(i["means3D"]), _ptr(i["shs"]), _ptr(i["colors_precomp"]), _ptr(i["opacities"])
+        g.scales, g.rotations, g.cov3D_precomp = _ptr(i["scales"]), _ptr(i["rotations"]), _ptr(i["cov3D_precomp"])
+        g.language_feature_precomp, g.shs_language, g.confidence = _ptr(i["language_feature_precomp"]), _ptr(i["shs_language"]), _ptr(i["confidence"])
+        self.v = _build_view(rs, P, M, self.extended, self._keep)
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.color = torch.empty((3, H, W), **f32)
+        self.radii = torch.empty((P,), dtype=torch.int32, device=dev)
+        o = self.o = Outputs()
+        o.color, o.radii = self.color.data_ptr(), _ptr(self.radii)
+        self.depth = self.alpha = self.feature = None
+        if self.extended:
+            self.depth, self.alpha, self.feature = torch.empty((1, H, W), **f32), torch.empty((1, H, W), **f32), torch.empty((3, H, W), **f32)
+            o.depth, o.alpha, o.feature = self.depth.data_ptr(), self.alpha.data_ptr(), self.feature.data_ptr()
+        u8 = dict(dtype=torch.uint8, device=dev)
+        self.geom = torch.empty((lib.b200gs_geom_bytes(P),), **u8)
+        self.img = torch.empty((lib.b200gs_image_bytes(W, H),), **u8)
+        self.binning = torch.empty((lib.b200gs_binning_bytes(self.capacity),), **u8)
+        ws = self.ws = Workspace()
+        ws.geom, ws.geom_bytes, ws.image, ws.image_bytes = self.geom.data_ptr(), self.geom.numel(), self.img.data_ptr(), self.img.numel()
+        ws.binning, ws.binning_bytes = self.binning.data_ptr(), self.binning.numel()
+        self.graph = None
+        self.with_backward = with_backward
+        if with_backward:
+            go = grads_out or {}
+            has = lambda t: t is not None
+            mk = lambda name, shape, cond=True: (go.get(name) if go.get(name) is not None else torch.empty(shape, **f32)) if cond else None
+            self.grads = dict(
+                means3D=mk("means3D", (P, 3)), means2D=mk("means2D", (P, 3)), opacities=mk("opacities", (P, 1)),
+                shs=mk("shs", (P, M, 3), has(i["shs"])), colors_precomp=mk("colors_precomp", (P, 3), has(i["colors_precomp"])),
+                scales=mk("scales", (P, 3), has(i["scales"])), rotations=mk("rotations", (P, 4), has(i["rotations"])),
+                cov3D=mk("cov3D", (P, 6), has(i["cov3D_precomp"])),
+                features=mk("features", (P, 3), self.extended and has(i["language_feature_precomp"])),
+                shs_language=mk("shs_language", (P, 3), self.extended and has(i["shs_language"])))
+            for k, t in self.grads.items():
+                if t is not None and (not t.is_contiguous() or t.dtype != torch.float32):
+                    raise RuntimeError(f"grads_out[{k}] must be a contiguous float32 tensor")
+            self.scratch = torch.empty((lib.b200gs_scratch_bytes(P),), **u8)
+            gr = self.gr = Grads()
+            G = self.grads
+            gr.dL_dmeans3D, gr.dL_dmeans2D, gr.dL_dshs, gr.dL_dcolors = _ptr(G["means3D"]), _ptr(G["means2D"]), _ptr(G["shs"]), _ptr(G["colors_precomp"])
+            gr.dL_dopacities, gr.dL_dscales, gr.dL_drotations, gr.dL_dcov3D = _ptr(G["opacities"]), _ptr(G["scales"]), _ptr(G["rotations"]), _ptr(G["cov3D"])
+            gr.dL_dfeatures, gr.dL_dshs_language, gr.scratch = _ptr(G["features"]), _ptr(G["shs_language"]), self.scratch.data_ptr()
+            self.cot = dict(color=torch.zeros((3, H, W), **f32))
+            go_ = self.go = GradOutputs()
+            go_.dL_dcolor = self.cot["color"].data_ptr()
+            if self.extended:
+                self.cot.update(depth=torch.zeros((1, H, W), **f32), alpha=torch.zeros((1, H, W), **f32),
+                                feature=torch.zeros((3, H, W), **f32))
+                go_.dL_ddepth, go_.dL_dalpha, go_.dL_dfeature = self.cot["depth"].data_ptr(), self.cot["alpha"].data_ptr(), self.cot["feature"].data_ptr()
+
+    def forward(self):
+        check(lib.b200gs_forward(C.byref(self.v), C.byref(self.g), C.byref(self.o), C.byref(self.ws),
+                                 C.c_int64(self.capacity), _stream()))
+
+    def backward(self):
+        check(lib.b200gs_backward(C.byref(self.v), C.byref(self.g), self.radii.data_ptr(), C.byref(self.ws),
+                                  C.c_int64(self.capacity), C.byref(self.go), C.byref(self.gr), _stream()))
+
+    def step(self):
+        """forward, then backward with the cotangents currently stored in `self.cot` (fill them between the two
+        yourself by calling forward()/backward() separately when the loss depends on the outputs)."""
+        self.forward()
+        if self.with_backward:
+            self.backward()
+
+    def capture(self, fn=None):
+        """Capture `fn` (default: self.step) into a CUDA graph on a side stream; returns self."""
+        fn = fn or self.step
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            fn()  # warm-up outside capture (lazy module loading must not happen while capturing)
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            fn()
+        return self
+
+    def replay(self):
+        self.graph.replay()
+
+    def status(self):
+        """(num_rendered, overflow) -- synchronizes the current stream."""
+        n, ov = C.c_int64(0), C.c_int32(0)
+        rc = lib.b200gs_forward_status(C.byref(self.ws), _stream(), C.byref(n), C.byref(ov))
+        if rc not in (0, -3):
+            check(rc)
+        return int(n.value), int(ov.value)

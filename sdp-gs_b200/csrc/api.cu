@@ -5,6 +5,8 @@
 // binning.cu / blend.cu.  Nothing here allocates device memory or touches the legacy default
 // stream: the caller owns the three byte workspaces and passes the stream.
 #include <atomic>
+#include <mutex>
+#include <vector>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -24,6 +26,33 @@ int fail(int code, const char* fmt, ...) {
 }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- optional per-stage timing (CUDA events on the launch stream), used by bench.py for the roofline ----
+enum Stage { ST_MEMSET = 0, ST_PREPROCESS, ST_DEPTH_SORT, ST_SCAN, ST_EMIT, ST_TILE_SORT, ST_RANGES, ST_BLEND_FWD,
+             ST_BLEND_BWD, ST_PREPROCESS_BWD, ST_COUNT };
+bool g_profile = false;
+struct Pending { int stage; cudaEvent_t a, b; };
+std::vector<Pending> g_pending;
+std::vector<cudaEvent_t> g_free_events;
+std::mutex g_prof_mu;
+double g_stage_ms[ST_COUNT] = {0};
+long long g_stage_n[ST_COUNT] = {0};
+
+cudaEvent_t get_event() {
+	if (!g_free_events.empty()) { cudaEvent_t e = g_free_events.back(); g_free_events.pop_back(); return e; }
+	cudaEvent_t e;
+	cudaEventCreate(&e);
+	return e;
+}
+struct StageScope {
+	cudaStream_t s; int stage; cudaEvent_t a;
+	StageScope(cudaStream_t s_, int st) : s(s_), stage(st), a(nullptr) {
+		if (g_profile) { std::lock_guard<std::mutex> l(g_prof_mu); a = get_event(); cudaEventRecord(a, s); }
+	}
+	~StageScope() {
+		if (a) { std::lock_guard<std::mutex> l(g_prof_mu); cudaEvent_t b = get_event(); cudaEventRecord(b, s); g_pending.push_back({stage, a, b}); }
+	}
+};
 
 template <typename T>
 void carve(char*& p, T*& out, size_t count) {
@@ -146,6 +175,26 @@ extern "C" {
 int b200gs_version(void) { return B200GS_VERSION; }
 const char* b200gs_last_error(void) { return g_err; }
 int64_t b200gs_launch_count(void) { return g_launches.load(); }
+void b200gs_profile_enable(int32_t on) { std::lock_guard<std::mutex> l(g_prof_mu); g_profile = on != 0; }
+int b200gs_profile_read(double* ms_out, int64_t* n_out, int32_t reset) {
+	std::lock_guard<std::mutex> l(g_prof_mu);
+	for (auto& p : g_pending) {
+		if (cudaEventSynchronize(p.b) != cudaSuccess) return fail(B200GS_E_CUDA, "profile event sync failed");
+		float ms = 0.f;
+		cudaEventElapsedTime(&ms, p.a, p.b);
+		g_stage_ms[p.stage] += ms;
+		g_stage_n[p.stage] += 1;
+		g_free_events.push_back(p.a);
+		g_free_events.push_back(p.b);
+	}
+	g_pending.clear();
+	for (int i = 0; i < ST_COUNT; i++) {
+		if (ms_out) ms_out[i] = g_stage_ms[i];
+		if (n_out) n_out[i] = g_stage_n[i];
+		if (reset) { g_stage_ms[i] = 0; g_stage_n[i] = 0; }
+	}
+	return 0;
+}
 void b200gs_abi_sizes(int64_t* out6) {
 	out6[0] = sizeof(b200gs_view_t); out6[1] = sizeof(b200gs_gaussians_t); out6[2] = sizeof(b200gs_outputs_t);
 	out6[3] = sizeof(b200gs_workspace_t); out6[4] = sizeof(b200gs_grad_outputs_t); out6[5] = sizeof(b200gs_grads_t);
@@ -192,13 +241,18 @@ int b200gs_forward_preprocess(const b200gs_view_t* v, const b200gs_gaussians_t* 
 	GeomState gs = geom_from_chunk(gbase, P);
 	ImageState is = image_from_chunk(reinterpret_cast<char*>(ws->image), v->width, v->height);
 	const size_t tiles = (size_t)((v->width + TILE_X - 1) / TILE_X) * ((v->height + TILE_Y - 1) / TILE_Y);
-	cudaMemsetAsync(gbase, 0, geom_zero_len(P), stream);
-	cudaMemsetAsync(is.ranges, 0, tiles * sizeof(uint2), stream);  // rasterizer_impl.cu:310
+	{
+		StageScope t(stream, ST_MEMSET);
+		cudaMemsetAsync(gbase, 0, geom_zero_len(P), stream);
+		cudaMemsetAsync(is.ranges, 0, tiles * sizeof(uint2), stream);  // rasterizer_impl.cu:310
+	}
 	if (P > 0) {
-		launch_preprocess_forward(*v, *g, out->radii, gs, stream);
+		{ StageScope t(stream, ST_PREPROCESS); launch_preprocess_forward(*v, *g, out->radii, gs, stream); }
 		if (int e = check_stage(v, stream, "preprocess")) return e;
-		launch_depth_order(gs, P, stream);
-		if (int e = check_stage(v, stream, "depth order / scan")) return e;
+		{ StageScope t(stream, ST_DEPTH_SORT); launch_depth_order(gs, P, stream); }
+		if (int e = check_stage(v, stream, "depth order")) return e;
+		{ StageScope t(stream, ST_SCAN); launch_offsets_scan(gs, P, stream); }
+		if (int e = check_stage(v, stream, "offsets scan")) return e;
 	}
 	if (num_rendered_host) {
 		unsigned long long n = 0;
@@ -225,13 +279,15 @@ int b200gs_forward_render(const b200gs_view_t* v, const b200gs_gaussians_t* g, c
 	BinningState bs = binning_from_chunk(reinterpret_cast<char*>(ws->binning), v->width, v->height, capacity);
 	resolve_sorted(v, bs);
 	if (P > 0 && capacity > 0) {
-		cudaMemsetAsync(ws->binning, 0, binning_zero_len(capacity), stream);
-		launch_emit(*v, gs, bs, P, capacity, stream);
+		{ StageScope t(stream, ST_MEMSET); cudaMemsetAsync(ws->binning, 0, binning_zero_len(capacity), stream); }
+		{ StageScope t(stream, ST_EMIT); launch_emit(*v, gs, bs, P, capacity, stream); }
 		if (int e = check_stage(v, stream, "duplicate-with-keys")) return e;
-		launch_tile_sort_and_ranges(*v, gs, bs, is, capacity, stream);
-		if (int e = check_stage(v, stream, "tile sort / ranges")) return e;
+		{ StageScope t(stream, ST_TILE_SORT); launch_tile_sort(*v, gs, bs, capacity, stream); }
+		if (int e = check_stage(v, stream, "tile sort")) return e;
+		{ StageScope t(stream, ST_RANGES); launch_tile_ranges(gs, bs, is, capacity, stream); }
+		if (int e = check_stage(v, stream, "tile ranges")) return e;
 	}
-	launch_blend_forward(*v, gs, bs, is, *out, stream);
+	{ StageScope t(stream, ST_BLEND_FWD); launch_blend_forward(*v, gs, bs, is, *out, stream); }
 	return check_stage(v, stream, "blend forward");
 }
 
@@ -270,10 +326,10 @@ int b200gs_backward(const b200gs_view_t* v, const b200gs_gaussians_t* g, const i
 	BinningState bs = binning_from_chunk(reinterpret_cast<char*>(ws->binning), v->width, v->height, capacity);
 	resolve_sorted(v, bs);
 	float* grec = reinterpret_cast<float*>(grads->scratch);
-	cudaMemsetAsync(grec, 0, b200gs_scratch_bytes(P), stream);
-	launch_blend_backward(*v, gs, bs, is, *gout, grec, stream);
+	{ StageScope t(stream, ST_MEMSET); cudaMemsetAsync(grec, 0, b200gs_scratch_bytes(P), stream); }
+	{ StageScope t(stream, ST_BLEND_BWD); launch_blend_backward(*v, gs, bs, is, *gout, grec, stream); }
 	if (int e = check_stage(v, stream, "blend backward")) return e;
-	launch_preprocess_backward(*v, *g, radii, gs, grec, *grads, stream);
+	{ StageScope t(stream, ST_PREPROCESS_BWD); launch_preprocess_backward(*v, *g, radii, gs, grec, *grads, stream); }
 	return check_stage(v, stream, "preprocess backward");
 }
 

@@ -351,6 +351,10 @@ void launch_depth_order(GeomState& gs, int P, cudaStream_t stream) {
 	// keys: key_a (written by preprocess), values: order (identity written by preprocess); 4 passes -> result in (key_a, order)
 	unsigned int* tickets = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(gs.hdr) + offsetof(GeomHeader, sort_ticket));
 	launch_radix_sort(gs.key_a, gs.key_b, gs.order, gs.val_b, P, nullptr, 32, gs.hist, gs.lookback, tickets, stream);
+}
+
+void launch_offsets_scan(GeomState& gs, int P, cudaStream_t stream) {
+	if (P <= 0) return;
 	scan_offsets_kernel<<<(unsigned)scan_tiles_for(P), SCAN_THREADS, 0, stream>>>(gs.order, gs.rect, gs.offsets, P, gs.scan_state, gs.hdr);
 	count_launch();
 }
@@ -362,8 +366,7 @@ void launch_emit(const b200gs_view_t& v, GeomState& gs, BinningState& bs, int P,
 	count_launch();
 }
 
-void launch_tile_sort_and_ranges(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
-                                 int64_t capacity, cudaStream_t stream) {
+void launch_tile_sort(const b200gs_view_t& v, GeomState& gs, BinningState& bs, int64_t capacity, cudaStream_t stream) {
 	const uint32_t gx = (v.width + TILE_X - 1) / TILE_X, gy = (v.height + TILE_Y - 1) / TILE_Y;
 	const int bit = (int)higher_msb(gx * gy);
 	const unsigned long long* n_dev = &gs.hdr->num_rendered;
@@ -372,6 +375,10 @@ void launch_tile_sort_and_ranges(const b200gs_view_t& v, GeomState& gs, BinningS
 	                                    bs.lookback, tickets, stream);
 	bs.sorted_keys = where ? bs.key_b : bs.key_a;
 	bs.sorted_vals = where ? bs.val_b : bs.val_a;
+}
+
+void launch_tile_ranges(GeomState& gs, BinningState& bs, ImageState& is, int64_t capacity, cudaStream_t stream) {
+	const unsigned long long* n_dev = &gs.hdr->num_rendered;
 	if (capacity > 0) {
 		tile_ranges_kernel<<<(unsigned)((capacity + 255) / 256), 256, 0, stream>>>(bs.sorted_keys, capacity, n_dev, is.ranges);
 		count_launch();

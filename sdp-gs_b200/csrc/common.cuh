@@ -96,10 +96,11 @@ void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, u
 int launch_radix_sort(uint32_t* key_a, uint32_t* key_b, uint32_t* val_a, uint32_t* val_b, int64_t n_max,
                       const unsigned long long* n_dev, int end_bit, uint32_t* hist /*[passes][256]*/,
                       uint32_t* lookback, unsigned int* tickets, cudaStream_t stream);
-void launch_depth_order(GeomState& gs, int P, cudaStream_t stream);                     // depth sort + offsets scan
+void launch_depth_order(GeomState& gs, int P, cudaStream_t stream);                     // stable sort of Gaussian ids by depth bits
+void launch_offsets_scan(GeomState& gs, int P, cudaStream_t stream);                    // inclusive scan of tiles touched, in depth order
 void launch_emit(const b200gs_view_t& v, GeomState& gs, BinningState& bs, int P, int64_t capacity, cudaStream_t stream);
-void launch_tile_sort_and_ranges(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
-                                 int64_t capacity, cudaStream_t stream);
+void launch_tile_sort(const b200gs_view_t& v, GeomState& gs, BinningState& bs, int64_t capacity, cudaStream_t stream);
+void launch_tile_ranges(GeomState& gs, BinningState& bs, ImageState& is, int64_t capacity, cudaStream_t stream);
 void launch_debug_keys(const b200gs_view_t& v, GeomState& gs, BinningState& bs, uint64_t* keys_out, int64_t L,
                        cudaStream_t stream);
 
