@@ -114,6 +114,7 @@ ImageState image_from_chunk(char* base, int W, int H) {
 	char* p = base;
 	const size_t N = (size_t)W * H, tiles = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
 	carve(p, s.ranges, tiles ? tiles : 1);
+	carve(p, s.tile_order, tiles ? tiles : 1);
 	carve(p, s.final_T, N ? N : 1);
 	carve(p, s.n_contrib, N ? N : 1);
 	s.bytes = align_up((size_t)(p - base), 256) + 256;
@@ -287,6 +288,8 @@ int b200gs_forward_render(const b200gs_view_t* v, const b200gs_gaussians_t* g, c
 		{ StageScope t(stream, ST_RANGES); launch_tile_ranges(gs, bs, is, capacity, stream); }
 		if (int e = check_stage(v, stream, "tile ranges")) return e;
 	}
+	{ StageScope t(stream, ST_RANGES); launch_tile_schedule(*v, is, stream); }
+	if (int e = check_stage(v, stream, "tile schedule")) return e;
 	{ StageScope t(stream, ST_BLEND_FWD); launch_blend_forward(*v, gs, bs, is, *out, stream); }
 	return check_stage(v, stream, "blend forward");
 }

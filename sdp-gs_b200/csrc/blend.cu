@@ -18,44 +18,9 @@
 //     per batch and one 16-byte vector reduction (red.global.add.v4.f32) per (tile, Gaussian,
 //     4 values).
 #include "common.cuh"
+#include "blend_common.cuh"
 
 namespace {
-
-struct PixelBlock {
-	float X0, X1, Y0, Y1;  // pixel-centre bounds of the warp's 8x4 block
-};
-
-// true when Gaussian (g0,g1,g2) cannot reach alpha >= 1/255 anywhere in the block
-__device__ __forceinline__ bool cull_block(const float4 g0, const float4 g1, const float nba, const PixelBlock& pb) {
-	const float mx = g0.x, my = g0.y, ca = g0.z, cb = g0.w, cc = g1.x, thr = g1.z, nbc = g1.w;
-	const float lx = pb.X0 - mx, hx = pb.X1 - mx, ly = pb.Y0 - my, hy = pb.Y1 - my;  // pixel - mean
-	const float ux = lx > 0.f ? lx : (hx < 0.f ? hx : 0.f);  // nearest offset in x (0 when the mean is inside)
-	const float uy = ly > 0.f ? ly : (hy < 0.f ? hy : 0.f);
-	float qmin = 0.f;
-	if (ux != 0.f || uy != 0.f) {
-		float q1 = 3.0e38f, q2 = 3.0e38f;
-		if (ux != 0.f) {  // edge x = const faces the mean: minimise over y
-			const float v = fminf(fmaxf(nbc * ux, ly), hy);
-			q1 = ca * ux * ux + 2.f * cb * ux * v + cc * v * v;
-		}
-		if (uy != 0.f) {
-			const float u = fminf(fmaxf(nba * uy, lx), hx);
-			q2 = ca * u * u + 2.f * cb * u * uy + cc * uy * uy;
-		}
-		qmin = fminf(q1, q2);
-	}
-	// rounding margin: the reference's own f32 evaluation of `power` at a pixel is off by a few ulps of
-	// its largest term, bounded by ca*DX^2 + cc*DY^2 over the block
-	const float DX = fmaxf(fabsf(lx), fabsf(hx)), DY = fmaxf(fabsf(ly), fabsf(hy));
-	const float margin = 2.0e-6f * (ca * DX * DX + cc * DY * DY) + 1.0e-4f;
-	const bool pd = ca > 0.f && cc > 0.f && (ca * cc - cb * cb) > 0.f;
-	return pd && (qmin > thr + margin);  // NaN anywhere -> false -> keep
-}
-
-__device__ __forceinline__ float pair_power(float dx, float dy, float ca, float cb, float cc) {
-	const float q = __fmaf_rn(dx, __fmul_rn(dx, ca), __fmul_rn(dy, __fmul_rn(dy, cc)));
-	return __fmaf_rn(q, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, cb)));
-}
 
 template <bool EXT>
 __global__ void __launch_bounds__(TILE_PIX) blend_forward_kernel(
@@ -99,7 +64,7 @@ __global__ void __launch_bounds__(TILE_PIX) blend_forward_kernel(
 		for (int m = 0; m * 32 < cnt; m++) {
 			const int jj = m * 32 + lane;
 			bool keep = false;
-			if (jj < cnt) keep = !cull_block(s_g0[jj], s_g1[jj], s_g2[jj].x, pb);
+			if (jj < cnt) keep = !cull_block(s_g0[jj], s_g1[jj], pb);
 			unsigned mask = __ballot_sync(0xFFFFFFFFu, keep);
 			while (mask) {
 				const int j = m * 32 + (__ffs(mask) - 1);
@@ -115,16 +80,16 @@ __global__ void __launch_bounds__(TILE_PIX) blend_forward_kernel(
 				const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
 				if (test_T < 0.0001f) { done = true; continue; }
 				const float4 g2 = s_g2[j];
-				C[0] = __fmaf_rn(T, __fmul_rn(alpha, g2.y), C[0]);
-				C[1] = __fmaf_rn(T, __fmul_rn(alpha, g2.z), C[1]);
-				C[2] = __fmaf_rn(T, __fmul_rn(alpha, g2.w), C[2]);
+				C[0] = __fmaf_rn(T, __fmul_rn(alpha, g2.x), C[0]);
+				C[1] = __fmaf_rn(T, __fmul_rn(alpha, g2.y), C[1]);
+				C[2] = __fmaf_rn(T, __fmul_rn(alpha, g2.z), C[2]);
 				if (EXT) {
 					const float4 g3 = s_g3[j];
-					C[3] = __fmaf_rn(T, __fmul_rn(alpha, g3.x), C[3]);
+					C[3] = __fmaf_rn(T, __fmul_rn(alpha, g2.w), C[3]);
 					C[4] = __fmaf_rn(T, alpha, C[4]);
-					C[5] = __fmaf_rn(T, __fmul_rn(alpha, g3.y), C[5]);
-					C[6] = __fmaf_rn(T, __fmul_rn(alpha, g3.z), C[6]);
-					C[7] = __fmaf_rn(T, __fmul_rn(alpha, g3.w), C[7]);
+					C[5] = __fmaf_rn(T, __fmul_rn(alpha, g3.x), C[5]);
+					C[6] = __fmaf_rn(T, __fmul_rn(alpha, g3.y), C[6]);
+					C[7] = __fmaf_rn(T, __fmul_rn(alpha, g3.z), C[7]);
 				}
 				T = test_T;
 				last_contributor = (uint32_t)(base + j + 1);
@@ -146,35 +111,6 @@ __global__ void __launch_bounds__(TILE_PIX) blend_forward_kernel(
 			out_feat[2 * HW + pix] = C[7];
 		}
 	}
-}
-
-// Sum 16 per-lane values over the warp; on return lane l (and l^1) holds the total of value l>>1.
-__device__ __forceinline__ float warp_reduce_scatter16(const float (&v)[16], unsigned lane) {
-	float a8[8], a4[4], a2[2];
-	const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
-#pragma unroll
-	for (int k = 0; k < 8; k++) {
-		const float send = h16 ? v[k] : v[k + 8], keep = h16 ? v[k + 8] : v[k];
-		a8[k] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 16);
-	}
-#pragma unroll
-	for (int k = 0; k < 4; k++) {
-		const float send = h8 ? a8[k] : a8[k + 4], keep = h8 ? a8[k + 4] : a8[k];
-		a4[k] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 8);
-	}
-#pragma unroll
-	for (int k = 0; k < 2; k++) {
-		const float send = h4 ? a4[k] : a4[k + 2], keep = h4 ? a4[k + 2] : a4[k];
-		a2[k] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 4);
-	}
-	const float send = h2 ? a2[0] : a2[1], keep = h2 ? a2[1] : a2[0];
-	float r = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 2);
-	r += __shfl_xor_sync(0xFFFFFFFFu, r, 1);
-	return r;
-}
-
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-	asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 template <bool EXT>
@@ -256,7 +192,7 @@ __global__ void __launch_bounds__(TILE_PIX) blend_backward_kernel(
 			for (int m = (cnt - 1) / 32; m >= 0; m--) {
 				const int jj = m * 32 + lane;
 				bool keep = false;
-				if (jj < cnt && (uint32_t)(base + jj) < wmax) keep = !cull_block(s_g0[jj], s_g1[jj], s_g2[jj].x, pb);
+				if (jj < cnt && (uint32_t)(base + jj) < wmax) keep = !cull_block(s_g0[jj], s_g1[jj], pb);
 				unsigned mask = __ballot_sync(0xFFFFFFFFu, keep);
 				while (mask) {
 					const int bit = 31 - __clz(mask);
@@ -278,10 +214,10 @@ __global__ void __launch_bounds__(TILE_PIX) blend_backward_kernel(
 						const float dchannel_dcolor = alpha * T;
 						const float4 g2 = s_g2[j];
 						float col[NC];
-						col[0] = g2.y; col[1] = g2.z; col[2] = g2.w;
+						col[0] = g2.x; col[1] = g2.y; col[2] = g2.z;
 						if (EXT) {
 							const float4 g3 = s_g3[j];
-							col[3] = g3.x; col[4] = 1.0f; col[5] = g3.y; col[6] = g3.z; col[7] = g3.w;
+							col[3] = g2.w; col[4] = 1.0f; col[5] = g3.x; col[6] = g3.y; col[7] = g3.z;
 						}
 						float dL_dalpha = 0.0f;
 #pragma unroll
@@ -333,7 +269,7 @@ __global__ void __launch_bounds__(TILE_PIX) blend_backward_kernel(
 
 }  // namespace
 
-void launch_blend_forward(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
+void launch_blend_forward_tile(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
                           const b200gs_outputs_t& out, cudaStream_t stream) {
 	const dim3 grid((v.width + TILE_X - 1) / TILE_X, (v.height + TILE_Y - 1) / TILE_Y);
 	if (v.extended)
@@ -345,7 +281,7 @@ void launch_blend_forward(const b200gs_view_t& v, GeomState& gs, BinningState& b
 	count_launch();
 }
 
-void launch_blend_backward(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
+void launch_blend_backward_tile(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
                            const b200gs_grad_outputs_t& gout, float* grec, cudaStream_t stream) {
 	const dim3 grid((v.width + TILE_X - 1) / TILE_X, (v.height + TILE_Y - 1) / TILE_Y);
 	if (v.extended)

@@ -11,9 +11,9 @@
 // Per-Gaussian "splat record": everything the blend kernels need, packed into 64 bytes so that a
 // tile's gather touches exactly two fully-used 32-B sectors per Gaussian.
 //   g0 = {x, y, conic.a, conic.b}
-//   g1 = {conic.c, opacity, cull_thr (= 2 ln(255 o)), -b/c}
-//   g2 = {-b/a, r, g, b}
-//   g3 = {z_view, f0, f1, f2}
+//   g1 = {conic.c, opacity, cull_thr (= 2 ln(255 o)), -b/c}      g0+g1: all a cull test and `power` need (one sector)
+//   g2 = {r, g, b, z_view}                                       payload, only touched by Gaussians that survive the cull
+//   g3 = {f0, f1, f2, 0}                                         (SDP-GS feature head)
 #define REC_FLOATS 16
 // Per-Gaussian gradient record accumulated by the blend backward (64 bytes):
 //   {dmean2D.x, dmean2D.y, dconic.a, dconic.b | dconic.c, dopacity, dr, dg | db, dz, df0, df1 | df2, -, -, -}
@@ -46,9 +46,10 @@ struct GeomState {
 };
 
 struct ImageState {
-	float* final_T;       // f32[N]
-	uint32_t* n_contrib;  // u32[N]
-	uint2* ranges;        // [tiles]
+	float* final_T;        // f32[N]
+	uint32_t* n_contrib;   // u32[N]
+	uint2* ranges;         // [tiles]
+	uint32_t* tile_order;  // [tiles] tile ids, heaviest (longest range) first: launch order of the blend units
 	size_t bytes;
 };
 
@@ -104,6 +105,7 @@ void launch_tile_ranges(GeomState& gs, BinningState& bs, ImageState& is, int64_t
 void launch_debug_keys(const b200gs_view_t& v, GeomState& gs, BinningState& bs, uint64_t* keys_out, int64_t L,
                        cudaStream_t stream);
 
+void launch_tile_schedule(const b200gs_view_t& v, ImageState& is, cudaStream_t stream);
 void launch_blend_forward(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
                           const b200gs_outputs_t& out, cudaStream_t stream);
 void launch_blend_backward(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,

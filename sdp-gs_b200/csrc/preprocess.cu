@@ -232,8 +232,8 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(
 				float4* rp = rec + 4 * (size_t)idx;
 				rp[0] = make_float4(pxi, pyi, ca, cb);
 				rp[1] = make_float4(cc, o, thr, -cb / cc);
-				rp[2] = make_float4(-cb / ca, rgb[0], rgb[1], rgb[2]);
-				rp[3] = make_float4(pz, f[0], f[1], f[2]);
+				rp[2] = make_float4(rgb[0], rgb[1], rgb[2], pz);
+				rp[3] = make_float4(f[0], f[1], f[2], 0.f);
 				clamped[idx] = (uint8_t)clamp_bits;
 				depths[idx] = pz;
 				out_radius = irad;

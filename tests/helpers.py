@@ -167,7 +167,7 @@ def run_product(inp, backward=True, cot=None, dev="cuda"):
     rec = np.where(vis[:, None], rec, 0).astype(np.float32)
     res["means2D"] = rec[:, 0:2].copy()
     res["conic_opacity"] = np.stack([rec[:, 2], rec[:, 3], rec[:, 4], rec[:, 5]], axis=1)
-    res["rgb"] = rec[:, 9:12].copy()
+    res["rgb"] = rec[:, 8:11].copy()
     res["rec"] = rec
     res["order"] = view(geom, off[5], np.uint32, P)
     off3 = (C.c_int64 * 3)()
