@@ -96,28 +96,47 @@ __global__ void __launch_bounds__(32) blend_forward_warp_kernel(
 #pragma unroll
 	for (int ch = 0; ch < NC; ch++) C[ch] = 0.f;
 
+	// Software pipeline over rounds of 32 list entries (one per lane), all in registers:
+	//   ids are loaded 3 rounds ahead, geometry (g0,g1) 2 rounds ahead, cull + payload 1 round ahead,
+	// so the only thing a round waits for is its own arithmetic -- the dependent chain
+	// point_list -> record -> payload (three L2 round trips) is off the unit's critical path.
+	const uint32_t NOID = 0xFFFFFFFFu;
+	auto load_id = [&](int base) -> uint32_t {
+		const int i = base + (int)lane;
+		return (i >= 0 && i < n) ? __ldg(point_list + u.range.x + i) : NOID;
+	};
+	auto load_geo = [&](uint32_t id, float4& g0, float4& g1) {
+		if (id != NOID) { const float4* r = rec + 4 * (size_t)id; g0 = __ldg(r); g1 = __ldg(r + 1); }
+	};
+	auto load_pay = [&](uint32_t id, bool keep, float4& g2, float4& g3) {
+		if (keep) { const float4* r = rec + 4 * (size_t)id; g2 = __ldg(r + 2); if (EXT) g3 = __ldg(r + 3); }
+	};
+	float4 xg0, xg1, xg2, xg3, yg0, yg1;
+	xg0 = xg1 = xg2 = xg3 = yg0 = yg1 = make_float4(0.f, 0.f, 0.f, 0.f);
+	uint32_t id_x = load_id(0), id_y = load_id(32), id_z = load_id(64);
+	load_geo(id_x, xg0, xg1);
+	load_geo(id_y, yg0, yg1);
+	bool xkeep = id_x != NOID && !cull_block(xg0, xg1, u.pb);
+	load_pay(id_x, xkeep, xg2, xg3);
+
 	for (int base = 0; base < n; base += 32) {
 		if (__all_sync(0xFFFFFFFFu, done)) break;
-		const int i = base + (int)lane;
-		bool keep = false;
-		float4 g0, g1, g2, g3;
-		if (i < n) {
-			const float4* r = rec + 4 * (size_t)point_list[u.range.x + i];
-			g0 = __ldg(r); g1 = __ldg(r + 1);
-			keep = !cull_block(g0, g1, u.pb);
-			if (keep) {
-				g2 = __ldg(r + 2);
-				if (EXT) g3 = __ldg(r + 3);
+		const uint32_t id_w = load_id(base + 96);                       // ids, round r+3
+		float4 zg0 = make_float4(0.f, 0.f, 0.f, 0.f), zg1 = zg0;
+		load_geo(id_z, zg0, zg1);                                       // geometry, round r+2
+		const bool ykeep = id_y != NOID && !cull_block(yg0, yg1, u.pb);   // cull + payload, round r+1
+		float4 yg2 = make_float4(0.f, 0.f, 0.f, 0.f), yg3 = yg2;
+		load_pay(id_y, ykeep, yg2, yg3);
+
+		unsigned mask = __ballot_sync(0xFFFFFFFFu, xkeep);              // consume round r
+		if (mask != 0) {
+			__syncwarp();  // readers of the previous round are done
+			if (xkeep) {
+				s_g0[lane] = xg0; s_g1[lane] = xg1; s_g2[lane] = xg2;
+				if (EXT) s_g3[lane] = xg3;
 			}
+			__syncwarp();
 		}
-		unsigned mask = __ballot_sync(0xFFFFFFFFu, keep);
-		if (mask == 0) continue;
-		__syncwarp();  // readers of the previous round are done
-		if (keep) {
-			s_g0[lane] = g0; s_g1[lane] = g1; s_g2[lane] = g2;
-			if (EXT) s_g3[lane] = g3;
-		}
-		__syncwarp();
 		while (mask) {
 			// up to 4 survivors at a time: their alphas are independent (ILP), only the T recurrence is serial
 			int jj[4];
@@ -165,6 +184,10 @@ __global__ void __launch_bounds__(32) blend_forward_warp_kernel(
 				}
 			}
 		}
+		// rotate the pipeline registers
+		xg0 = yg0; xg1 = yg1; xg2 = yg2; xg3 = yg3; xkeep = ykeep;
+		yg0 = zg0; yg1 = zg1;
+		id_y = id_z; id_z = id_w;
 	}
 	if (u.inside) {
 		const size_t pix = (size_t)u.py * W + u.px, HW = (size_t)H * W;
@@ -227,30 +250,45 @@ __global__ void __launch_bounds__(32) blend_backward_warp_kernel(
 	for (int ch = 0; ch < NC; ch++) { accum_rec[ch] = 0.f; last_color[ch] = 0.f; }
 	float last_alpha = 0.f;
 
-	// list positions [0, wmax) back to front, 32 per round
-	for (int base = (int)((wmax - 1) & ~31u); base >= 0; base -= 32) {
+	// list positions [0, wmax) back to front, 32 per round, with the same 3-deep register pipeline as the
+	// forward (ids 3 rounds ahead, geometry 2, cull + payload 1)
+	const uint32_t NOID = 0xFFFFFFFFu;
+	auto load_id = [&](int base) -> uint32_t {
 		const int i = base + (int)lane;
-		bool keep = false;
-		float4 g0, g1, g2, g3;
-		uint32_t id = 0;
-		if ((uint32_t)i < wmax) {
-			id = point_list[u.range.x + i];
-			const float4* r = rec + 4 * (size_t)id;
-			g0 = __ldg(r); g1 = __ldg(r + 1);
-			keep = !cull_block(g0, g1, u.pb);
-			if (keep) {
-				g2 = __ldg(r + 2);
-				if (EXT) g3 = __ldg(r + 3);
+		return (base >= 0 && (uint32_t)i < wmax) ? __ldg(point_list + u.range.x + i) : NOID;
+	};
+	auto load_geo = [&](uint32_t id, float4& g0, float4& g1) {
+		if (id != NOID) { const float4* r = rec + 4 * (size_t)id; g0 = __ldg(r); g1 = __ldg(r + 1); }
+	};
+	auto load_pay = [&](uint32_t id, bool keep, float4& g2, float4& g3) {
+		if (keep) { const float4* r = rec + 4 * (size_t)id; g2 = __ldg(r + 2); if (EXT) g3 = __ldg(r + 3); }
+	};
+	const int base0 = (int)((wmax - 1) & ~31u);
+	float4 xg0, xg1, xg2, xg3, yg0, yg1;
+	xg0 = xg1 = xg2 = xg3 = yg0 = yg1 = make_float4(0.f, 0.f, 0.f, 0.f);
+	uint32_t id_x = load_id(base0), id_y = load_id(base0 - 32), id_z = load_id(base0 - 64);
+	load_geo(id_x, xg0, xg1);
+	load_geo(id_y, yg0, yg1);
+	bool xkeep = id_x != NOID && !cull_block(xg0, xg1, u.pb);
+	load_pay(id_x, xkeep, xg2, xg3);
+
+	for (int base = base0; base >= 0; base -= 32) {
+		const uint32_t id_w = load_id(base - 96);
+		float4 zg0 = make_float4(0.f, 0.f, 0.f, 0.f), zg1 = zg0;
+		load_geo(id_z, zg0, zg1);
+		const bool ykeep = id_y != NOID && !cull_block(yg0, yg1, u.pb);
+		float4 yg2 = make_float4(0.f, 0.f, 0.f, 0.f), yg3 = yg2;
+		load_pay(id_y, ykeep, yg2, yg3);
+
+		unsigned mask = __ballot_sync(0xFFFFFFFFu, xkeep);
+		if (mask != 0) {
+			__syncwarp();
+			if (xkeep) {
+				s_g0[lane] = xg0; s_g1[lane] = xg1; s_g2[lane] = xg2; s_id[lane] = id_x;
+				if (EXT) s_g3[lane] = xg3;
 			}
+			__syncwarp();
 		}
-		unsigned mask = __ballot_sync(0xFFFFFFFFu, keep);
-		if (mask == 0) continue;
-		__syncwarp();
-		if (keep) {
-			s_g0[lane] = g0; s_g1[lane] = g1; s_g2[lane] = g2; s_id[lane] = id;
-			if (EXT) s_g3[lane] = g3;
-		}
-		__syncwarp();
 		while (mask) {
 			const int j = 31 - __clz(mask);
 			mask &= ~(1u << j);
@@ -309,6 +347,9 @@ __global__ void __launch_bounds__(32) blend_backward_warp_kernel(
 			// lanes 0,2,..,2(NV-1) hold values 0..NV-1: one reduction instruction covering the 64-byte record
 			if ((lane & 1) == 0 && (lane >> 1) < NV) atomicAdd(grec + (size_t)s_id[j] * GREC_FLOATS + (lane >> 1), tot);
 		}
+		xg0 = yg0; xg1 = yg1; xg2 = yg2; xg3 = yg3; xkeep = ykeep; id_x = id_y;
+		yg0 = zg0; yg1 = zg1;
+		id_y = id_z; id_z = id_w;
 	}
 }
 
