@@ -126,7 +126,7 @@ const char* b200gs_last_error(void);
 
 size_t b200gs_geom_bytes(int32_t P);
 size_t b200gs_image_bytes(int32_t width, int32_t height);
-size_t b200gs_binning_bytes(int64_t capacity); /* capacity = max number of (Gaussian,tile) instances */
+size_t b200gs_binning_bytes(int64_t capacity); /* capacity = max number of (Gaussian,tile) instances, < 2^30 */
 size_t b200gs_scratch_bytes(int32_t P);
 
 /* Stage 1 of the forward: preprocess, depth ordering, instance count.  Needs ws->geom and
@@ -162,7 +162,7 @@ int b200gs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix
 /* Byte offsets of the decodable arrays inside each workspace.
  * geom   : [0] header, [1] depths f32[P], [2] rect u16[P][4] (x0,y0,x1,y1), [3] record f32[P][16],
  *          [4] clamped u8[P] (bit c = colour channel c clamped), [5] order u32[P] (Gaussian ids by
- *          (depth bits, id)), [6] offsets u32[P] (inclusive scan of tiles touched, in `order` order)
+ *          (depth bits, id)), [6] sorted depth keys u32[P] (0xFFFFFFFF for culled Gaussians)
  * image  : [0] final_T f32[N], [1] n_contrib u32[N], [2] ranges u32[tiles][2]
  * binning: [0] point_list u32[L] (sorted), [1] tile ids u32[L] (sorted)   -- valid after forward_render */
 void b200gs_geom_layout(int32_t P, int64_t* offsets7);

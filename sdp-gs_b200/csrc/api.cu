@@ -96,7 +96,6 @@ GeomState geom_from_chunk(char* base, int P) {
 	carve(p, g.rec, 4 * n);
 	carve(p, g.clamped, n);
 	carve(p, g.order, n);
-	carve(p, g.offsets, n);
 	carve(p, g.key_a, n);
 	carve(p, g.key_b, n);
 	carve(p, g.val_b, n);
@@ -135,11 +134,6 @@ BinningState binning_from_chunk(char* base, int W, int H, int64_t capacity) {
 	b.sorted_vals = b.val_a;
 	b.bytes = align_up((size_t)(p - base), 256) + 256;
 	return b;
-}
-
-static size_t binning_zero_len(int64_t capacity) {
-	BinningState b = binning_from_chunk(nullptr, 0, 0, capacity);
-	return reinterpret_cast<size_t>(b.key_a);
 }
 
 static void resolve_sorted(const b200gs_view_t* v, BinningState& bs) {
@@ -214,7 +208,7 @@ void b200gs_geom_layout(int32_t P, int64_t* off) {
 	off[3] = (int64_t)reinterpret_cast<size_t>(g.rec);
 	off[4] = (int64_t)reinterpret_cast<size_t>(g.clamped);
 	off[5] = (int64_t)reinterpret_cast<size_t>(g.order);
-	off[6] = (int64_t)reinterpret_cast<size_t>(g.offsets);
+	off[6] = (int64_t)reinterpret_cast<size_t>(g.key_a);
 }
 void b200gs_image_layout(int32_t width, int32_t height, int64_t* off) {
 	ImageState s = image_from_chunk(nullptr, width, height);
@@ -245,15 +239,13 @@ int b200gs_forward_preprocess(const b200gs_view_t* v, const b200gs_gaussians_t* 
 	{
 		StageScope t(stream, ST_MEMSET);
 		cudaMemsetAsync(gbase, 0, geom_zero_len(P), stream);
-		cudaMemsetAsync(is.ranges, 0, tiles * sizeof(uint2), stream);  // rasterizer_impl.cu:310
+		if (P == 0) cudaMemsetAsync(is.ranges, 0, tiles * sizeof(uint2), stream);  // otherwise zeroed by the preprocess kernel (rasterizer_impl.cu:310)
 	}
 	if (P > 0) {
-		{ StageScope t(stream, ST_PREPROCESS); launch_preprocess_forward(*v, *g, out->radii, gs, stream); }
+		{ StageScope t(stream, ST_PREPROCESS); launch_preprocess_forward(*v, *g, out->radii, gs, is, stream); }
 		if (int e = check_stage(v, stream, "preprocess")) return e;
 		{ StageScope t(stream, ST_DEPTH_SORT); launch_depth_order(gs, P, stream); }
 		if (int e = check_stage(v, stream, "depth order")) return e;
-		{ StageScope t(stream, ST_SCAN); launch_offsets_scan(gs, P, stream); }
-		if (int e = check_stage(v, stream, "offsets scan")) return e;
 	}
 	if (num_rendered_host) {
 		unsigned long long n = 0;
@@ -271,7 +263,7 @@ int b200gs_forward_render(const b200gs_view_t* v, const b200gs_gaussians_t* g, c
 	if (!out || !out->color) return fail(B200GS_E_ARG, "color output is required");
 	if (v->extended && (!out->depth || !out->alpha || !out->feature)) return fail(B200GS_E_ARG, "extended outputs are required");
 	if (capacity < 0) return fail(B200GS_E_ARG, "negative capacity");
-	if (capacity > 0xFFFFFFFFll) return fail(B200GS_E_ARG, "capacity exceeds 32-bit instance offsets");
+	if (capacity >= (1ll << 30)) return fail(B200GS_E_ARG, "capacity exceeds 2^30 instances (30-bit look-back counters)");
 	if (!ws->binning || ws->binning_bytes < b200gs_binning_bytes(capacity)) return fail(B200GS_E_ARG, "binning workspace too small");
 	cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
 	const int P = g->P;
@@ -280,16 +272,13 @@ int b200gs_forward_render(const b200gs_view_t* v, const b200gs_gaussians_t* g, c
 	BinningState bs = binning_from_chunk(reinterpret_cast<char*>(ws->binning), v->width, v->height, capacity);
 	resolve_sorted(v, bs);
 	if (P > 0 && capacity > 0) {
-		{ StageScope t(stream, ST_MEMSET); cudaMemsetAsync(ws->binning, 0, binning_zero_len(capacity), stream); }
-		{ StageScope t(stream, ST_EMIT); launch_emit(*v, gs, bs, P, capacity, stream); }
-		if (int e = check_stage(v, stream, "duplicate-with-keys")) return e;
+		{ StageScope t(stream, ST_EMIT); launch_scan_emit(*v, gs, bs, P, capacity, stream); }
+		if (int e = check_stage(v, stream, "instance offsets / duplicate-with-keys")) return e;
 		{ StageScope t(stream, ST_TILE_SORT); launch_tile_sort(*v, gs, bs, capacity, stream); }
 		if (int e = check_stage(v, stream, "tile sort")) return e;
-		{ StageScope t(stream, ST_RANGES); launch_tile_ranges(gs, bs, is, capacity, stream); }
-		if (int e = check_stage(v, stream, "tile ranges")) return e;
 	}
-	{ StageScope t(stream, ST_RANGES); launch_tile_schedule(*v, is, stream); }
-	if (int e = check_stage(v, stream, "tile schedule")) return e;
+	{ StageScope t(stream, ST_RANGES); launch_tile_ranges(*v, gs, bs, is, (P > 0) ? capacity : 0, stream); }
+	if (int e = check_stage(v, stream, "tile ranges / schedule")) return e;
 	{ StageScope t(stream, ST_BLEND_FWD); launch_blend_forward(*v, gs, bs, is, *out, stream); }
 	return check_stage(v, stream, "blend forward");
 }

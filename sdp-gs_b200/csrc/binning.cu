@@ -1,5 +1,5 @@
-// b200gs -- ordering stages: depth order of the Gaussians, instance offsets, duplicate-with-keys,
-// tile sort, tile ranges.
+// b200gs -- ordering stages: depth order of the Gaussians, instance offsets + duplicate-with-keys,
+// tile sort, tile ranges + blend schedule.
 //
 // The reference sorts all L (Gaussian, tile) instances by a 64-bit key (tile << 32 | depth bits)
 // with a stable LSD radix sort over 32 + getHigherMsb(tiles) bits (DGR/cuda_rasterizer/
@@ -13,7 +13,9 @@
 //
 // The radix pass is a single-read "onesweep" pass: per-tile digit counts are chained between
 // CTAs with decoupled look-back (one 32-bit status word per (tile, digit)), tile ids are handed
-// out by an atomic ticket so a CTA only ever waits on CTAs that already started.
+// out by an atomic ticket so a CTA only ever waits on CTAs that already started.  The digit
+// histograms a pass needs are produced by the kernel that writes the keys (preprocess for the
+// depth keys, scan_emit for the tile keys), not by a separate read of the keys.
 #include <cstddef>
 #include "common.cuh"
 
@@ -23,6 +25,7 @@ constexpr uint32_t FLAG_LOCAL = 1u << 30;   // word holds this tile's own count
 constexpr uint32_t FLAG_INCL = 2u << 30;    // word holds the inclusive count over tiles [0..t]
 constexpr uint32_t FLAG_MASK = 3u << 30;
 constexpr uint32_t VALUE_MASK = ~FLAG_MASK;
+constexpr int LOOKBACK_WINDOW = 8;          // predecessors inspected per step (independent loads in flight)
 
 __device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 __device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
@@ -33,27 +36,36 @@ __device__ __forceinline__ int64_t load_count(const unsigned long long* n_dev, i
 	return n < (unsigned long long)n_max ? (int64_t)n : n_max;
 }
 
-// Digit histograms of every pass in one read of the keys: hist[pass][256].
-__global__ void __launch_bounds__(256) radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t n_max,
-                                                         const unsigned long long* __restrict__ n_dev, int end_bit,
-                                                         uint32_t* __restrict__ hist) {
-	__shared__ uint32_t s_hist[4][256];
-	const int passes = (end_bit + 7) / 8;
-	for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) (&s_hist[0][0])[i] = 0;
-	__syncthreads();
-	const int64_t n = load_count(n_dev, n_max);
-	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-		const uint32_t k = keys[i];
-		for (int p = 0; p < passes; p++) {
-			const int bits = min(8, end_bit - 8 * p);
-			atomicAdd(&s_hist[p][(k >> (8 * p)) & ((1u << bits) - 1)], 1u);
+// Exclusive prefix of `mine` over tiles [0, tile) for one status column (stride words apart), publishing this
+// tile's LOCAL then INCLUSIVE word.  Predecessors are inspected LOOKBACK_WINDOW at a time so the walk is a few
+// independent load batches instead of one dependent L2 round trip per predecessor.
+__device__ __forceinline__ uint32_t lookback_exclusive(uint32_t* __restrict__ column, size_t stride, uint32_t tile, uint32_t mine) {
+	uint32_t* my = column + (size_t)tile * stride;
+	if (tile == 0) {
+		st_volatile(my, mine | FLAG_INCL);
+		return 0;
+	}
+	st_volatile(my, mine | FLAG_LOCAL);
+	uint32_t excl = 0;
+	int64_t t = (int64_t)tile - 1;
+	while (true) {
+		uint32_t w[LOOKBACK_WINDOW];
+#pragma unroll
+		for (int i = 0; i < LOOKBACK_WINDOW; i++) w[i] = (t - i >= 0) ? ld_volatile(column + (size_t)(t - i) * stride) : FLAG_INCL;
+		bool found = false;
+#pragma unroll
+		for (int i = 0; i < LOOKBACK_WINDOW; i++) {
+			if (!found) {
+				while ((w[i] & FLAG_MASK) == 0) w[i] = ld_volatile(column + (size_t)(t - i) * stride);
+				excl += w[i] & VALUE_MASK;
+				found = (w[i] & FLAG_INCL) != 0;
+			}
 		}
+		if (found) break;
+		t -= LOOKBACK_WINDOW;
 	}
-	__syncthreads();
-	for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) {
-		const uint32_t c = (&s_hist[0][0])[i];
-		if (c) atomicAdd(hist + i, c);
-	}
+	st_volatile(my, (excl + mine) | FLAG_INCL);
+	return excl;
 }
 
 template <int ITEMS>
@@ -70,6 +82,7 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(
 	__shared__ uint32_t s_digit_base[256];
 	__shared__ uint32_t s_keys[TILE];
 	__shared__ uint32_t s_vals[TILE];
+	__shared__ uint32_t s_g[WARPS], s_l[WARPS];
 	__shared__ uint32_t s_tile;
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -110,47 +123,31 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(
 	__syncthreads();
 
 	// 2. per digit (thread d): exclusive scan over warps, tile total, decoupled look-back
-	uint32_t tile_count = 0;
 	{
 		const int d = tid;
+		uint32_t tile_count = 0;
 #pragma unroll
 		for (int w = 0; w < WARPS; w++) {
 			const uint32_t t = s_warp_hist[w][d];
 			s_warp_hist[w][d] = tile_count;
 			tile_count += t;
 		}
-		uint32_t excl = 0;
-		uint32_t* my = lookback + (size_t)tile * 256 + d;
-		if (tile == 0) {
-			st_volatile(my, tile_count | FLAG_INCL);
-		} else {
-			st_volatile(my, tile_count | FLAG_LOCAL);
-			int64_t t = (int64_t)tile - 1;
-			while (true) {
-				uint32_t w;
-				do { w = ld_volatile(lookback + (size_t)t * 256 + d); } while ((w & FLAG_MASK) == 0);
-				excl += w & VALUE_MASK;
-				if (w & FLAG_INCL) break;
-				t--;
-			}
-			st_volatile(my, (excl + tile_count) | FLAG_INCL);
-		}
+		const uint32_t excl = lookback_exclusive(lookback + d, 256, tile, tile_count);
 		// exclusive scan of the global digit histogram and of the tile counts across the 256 digits
-		uint32_t g = hist[d], l = tile_count;
+		const uint32_t g = hist[d], l = tile_count;
 		uint32_t gi = g, li = l;
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1) {
 			const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, gi, o), b = __shfl_up_sync(0xFFFFFFFFu, li, o);
 			if (lane >= o) { gi += a; li += b; }
 		}
-		__shared__ uint32_t s_g[WARPS], s_l[WARPS];
 		if (lane == 31) { s_g[warp] = gi; s_l[warp] = li; }
 		__syncthreads();
 		uint32_t gw = 0, lw = 0;
 		for (int w = 0; w < warp; w++) { gw += s_g[w]; lw += s_l[w]; }
 		const uint32_t g_excl = gw + gi - g, l_excl = lw + li - l;
 		s_local_off[d] = l_excl;
-		s_digit_base[d] = g_excl + excl - l_excl;  // global position = s_digit_base[d] + local position
+		s_digit_base[d] = g_excl + excl - l_excl;  // global position = s_digit_base[d] + local position (mod 2^32)
 	}
 	__syncthreads();
 
@@ -169,40 +166,53 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(
 	for (int i = tid; i < tile_n; i += SORT_THREADS) {
 		const uint32_t k = s_keys[i];
 		const uint32_t d = (k >> shift) & dmask;
-		const uint32_t dst = s_digit_base[d] + (uint32_t)i;  // mod 2^32: s_digit_base may have wrapped
+		const uint32_t dst = s_digit_base[d] + (uint32_t)i;
 		keys_out[dst] = k;
 		vals_out[dst] = s_vals[i];
 	}
 }
 
-// Inclusive scan of tiles-touched in depth order (K2 of the reference, rasterizer_impl.cu:277, fused
-// with the gather through `order`), single pass with decoupled look-back.
-__global__ void __launch_bounds__(SCAN_THREADS) scan_offsets_kernel(
-	const uint32_t* __restrict__ order, const ushort4* __restrict__ rect, uint32_t* __restrict__ offsets, int P,
-	unsigned long long* __restrict__ state, GeomHeader* __restrict__ hdr)
+// K2 + K3 fused: inclusive scan of tiles-touched in depth order (rasterizer_impl.cu:277) with decoupled
+// look-back, and duplicateWithKeys (rasterizer_impl.cu:70-111) straight from the scanned offsets.  The depth
+// half of the reference's key is implied by the emission order, so only the tile id is written as sort key.
+// Also: digit histograms of the tile ids for the tile sort, and the zeroing of its look-back words.
+constexpr int EMIT_THREADS = 256;
+constexpr int EMIT_ITEMS = 4;
+constexpr uint32_t EMIT_SMALL = 12;
+
+__global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(
+	const uint32_t* __restrict__ order, const ushort4* __restrict__ rect, int P, uint32_t grid_x, int64_t capacity,
+	int tile_bits, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ scan_state,
+	uint32_t* __restrict__ tile_hist /*[4][256]*/, uint32_t* __restrict__ zero_words, size_t zero_count,
+	GeomHeader* __restrict__ hdr)
 {
-	constexpr unsigned long long F_LOCAL = 1ull << 62, F_INCL = 2ull << 62, F_MASK = 3ull << 62;
-	constexpr int TILE = SCAN_THREADS * SCAN_ITEMS;
-	__shared__ uint32_t s_warp[SCAN_THREADS / 32];
-	__shared__ unsigned long long s_prefix;
+	constexpr int TILE = EMIT_THREADS * EMIT_ITEMS;
+	__shared__ uint32_t s_hist[4][256];
+	__shared__ uint32_t s_warp[EMIT_THREADS / 32];
+	__shared__ uint32_t s_prefix;
 	__shared__ uint32_t s_tile;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int passes = (tile_bits + 7) / 8;
 	if (tid == 0) s_tile = atomicAdd(&hdr->scan_ticket, 1u);
+	for (int i = tid; i < 4 * 256; i += EMIT_THREADS) (&s_hist[0][0])[i] = 0;
+	// zero the tile sort's look-back words (they are first read by the next kernel)
+	for (size_t i = (size_t)blockIdx.x * EMIT_THREADS + tid; i < zero_count; i += (size_t)gridDim.x * EMIT_THREADS) zero_words[i] = 0;
 	__syncthreads();
 	const uint32_t tile = s_tile;
-	const int base = tile * TILE + tid * SCAN_ITEMS;
-	uint32_t v[SCAN_ITEMS];
+	const int base = tile * TILE + tid * EMIT_ITEMS;
+
+	uint32_t g[EMIT_ITEMS], n[EMIT_ITEMS];
+	ushort4 r[EMIT_ITEMS];
 	uint32_t sum = 0;
 #pragma unroll
-	for (int j = 0; j < SCAN_ITEMS; j++) {
-		const int i = base + j;
-		uint32_t n = 0;
-		if (i < P) {
-			const ushort4 r = rect[order[i]];
-			n = (uint32_t)(r.z - r.x) * (uint32_t)(r.w - r.y);
+	for (int k = 0; k < EMIT_ITEMS; k++) {
+		g[k] = 0; n[k] = 0; r[k] = make_ushort4(0, 0, 0, 0);
+		if (base + k < P) {
+			g[k] = order[base + k];
+			r[k] = rect[g[k]];
+			n[k] = (uint32_t)(r[k].z - r[k].x) * (uint32_t)(r[k].w - r[k].y);
 		}
-		sum += n;
-		v[j] = sum;  // inclusive within the thread
+		sum += n[k];
 	}
 	uint32_t inc = sum;
 #pragma unroll
@@ -213,96 +223,105 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_offsets_kernel(
 	if (lane == 31) s_warp[warp] = inc;
 	__syncthreads();
 	uint32_t wpre = 0, total = 0;
-	for (int w = 0; w < SCAN_THREADS / 32; w++) {
+	for (int w = 0; w < EMIT_THREADS / 32; w++) {
 		if (w < warp) wpre += s_warp[w];
 		total += s_warp[w];
 	}
 	if (tid == 0) {
-		unsigned long long excl = 0;
-		volatile unsigned long long* st = state;
-		if (tile == 0) {
-			st[0] = (unsigned long long)total | F_INCL;
-		} else {
-			st[tile] = (unsigned long long)total | F_LOCAL;
-			int64_t t = (int64_t)tile - 1;
-			while (true) {
-				unsigned long long w;
-				do { w = st[t]; } while ((w & F_MASK) == 0);
-				excl += w & ~F_MASK;
-				if (w & F_INCL) break;
-				t--;
-			}
-			st[tile] = (excl + total) | F_INCL;
-		}
+		const uint32_t excl = lookback_exclusive(scan_state, 1, tile, total);
 		s_prefix = excl;
-		if ((int64_t)(tile + 1) * TILE >= P) hdr->num_rendered = excl + total;  // last tile
+		if ((int64_t)(tile + 1) * TILE >= P) {  // last tile: instance count, overflow flag
+			const unsigned long long L = (unsigned long long)excl + total;
+			hdr->num_rendered = L;
+			if (L > (unsigned long long)capacity) atomicOr(&hdr->overflow, 1u);
+		}
 	}
 	__syncthreads();
-	const uint32_t thread_excl = (uint32_t)s_prefix + wpre + inc - sum;
+	uint32_t start = s_prefix + wpre + inc - sum;  // exclusive offset of this thread's first item
+
+	const uint32_t m0 = (1u << min(8, tile_bits)) - 1u;
+	auto put = [&](uint32_t pos, uint32_t key, uint32_t val) {
+		if ((int64_t)pos < capacity) {
+			keys[pos] = key;
+			vals[pos] = val;
+			atomicAdd(&s_hist[0][key & m0], 1u);
+			for (int p = 1; p < passes; p++) atomicAdd(&s_hist[p][(key >> (8 * p)) & ((1u << min(8, tile_bits - 8 * p)) - 1u)], 1u);
+		}
+	};
 #pragma unroll
-	for (int j = 0; j < SCAN_ITEMS; j++) {
-		const int i = base + j;
-		if (i < P) offsets[i] = thread_excl + v[j];
+	for (int k = 0; k < EMIT_ITEMS; k++) {
+		if (n[k] > 0 && n[k] <= EMIT_SMALL) {
+			uint32_t x = r[k].x, y = r[k].y;
+			for (uint32_t j = 0; j < n[k]; j++) {
+				put(start + j, y * grid_x + x, g[k]);
+				if (++x == r[k].z) { x = r[k].x; y++; }
+			}
+		}
+		// large footprints: the whole warp emits one Gaussian's tiles together
+		uint32_t big = __ballot_sync(0xFFFFFFFFu, n[k] > EMIT_SMALL);
+		while (big) {
+			const int src = __ffs(big) - 1;
+			big &= big - 1;
+			const uint32_t bg = __shfl_sync(0xFFFFFFFFu, g[k], src), bn = __shfl_sync(0xFFFFFFFFu, n[k], src);
+			const uint32_t bstart = __shfl_sync(0xFFFFFFFFu, start, src);
+			const uint32_t bx0 = __shfl_sync(0xFFFFFFFFu, (uint32_t)r[k].x, src), by0 = __shfl_sync(0xFFFFFFFFu, (uint32_t)r[k].y, src);
+			const uint32_t bw = __shfl_sync(0xFFFFFFFFu, (uint32_t)(r[k].z - r[k].x), src);
+			for (uint32_t j = lane; j < bn; j += 32) put(bstart + j, (by0 + j / bw) * grid_x + (bx0 + j % bw), bg);
+		}
+		start += n[k];
+	}
+	__syncthreads();
+	for (int i = tid; i < passes * 256; i += EMIT_THREADS) {
+		const uint32_t c = (&s_hist[0][0])[i];
+		if (c) atomicAdd(tile_hist + i, c);
 	}
 }
 
-// K3: duplicateWithKeys (rasterizer_impl.cu:70-111) in depth order.  The depth half of the
-// reference's key is implied by the emission order, so only the tile id is written as sort key.
-__global__ void __launch_bounds__(256) emit_instances_kernel(
-	const uint32_t* __restrict__ order, const uint32_t* __restrict__ offsets, const ushort4* __restrict__ rect, int P,
-	uint32_t grid_x, int64_t capacity, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, GeomHeader* __restrict__ hdr)
+// K5: identifyTileRanges (rasterizer_impl.cu:116-138; `ranges` zero-initialised by the preprocess kernel, :310),
+// and -- by the last CTA to finish -- the launch order of the blend units: tile ids, heaviest (longest range)
+// first.  key = 7 bits (position of the leading one and the next two bits of the range length); counting sort
+// by descending key; order inside a bucket is arbitrary (blend units are independent of each other).
+__global__ void __launch_bounds__(256) tile_ranges_schedule_kernel(
+	const uint32_t* __restrict__ tile_keys, int64_t n_max, const unsigned long long* __restrict__ n_dev,
+	uint2* __restrict__ ranges, int tiles, uint32_t* __restrict__ order, unsigned int* __restrict__ done_counter)
 {
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	const unsigned lane = threadIdx.x & 31;
-	uint32_t g = 0, n = 0, start = 0;
-	ushort4 r = make_ushort4(0, 0, 0, 0);
-	if (i < P) {
-		g = order[i];
-		r = rect[g];
-		n = (uint32_t)(r.z - r.x) * (uint32_t)(r.w - r.y);
-		start = offsets[i] - n;
-		if (i == P - 1 && (unsigned long long)offsets[i] > (unsigned long long)capacity) atomicOr(&hdr->overflow, 1u);
-	}
-	constexpr uint32_t SMALL = 12;
-	if (n > 0 && n <= SMALL) {
-		const uint32_t w = r.z - r.x;
-		uint32_t x = r.x, y = r.y;
-		for (uint32_t k = 0; k < n; k++) {
-			const uint32_t pos = start + k;
-			if ((int64_t)pos < capacity) { keys[pos] = y * grid_x + x; vals[pos] = g; }
-			if (++x == r.z) { x = r.x; y++; }
-		}
-		(void)w;
-	}
-	// large footprints: the whole warp emits one Gaussian's tiles together
-	uint32_t big = __ballot_sync(0xFFFFFFFFu, n > SMALL);
-	while (big) {
-		const int src = __ffs(big) - 1;
-		big &= big - 1;
-		const uint32_t bg = __shfl_sync(0xFFFFFFFFu, g, src), bn = __shfl_sync(0xFFFFFFFFu, n, src);
-		const uint32_t bstart = __shfl_sync(0xFFFFFFFFu, start, src);
-		const uint32_t bx0 = __shfl_sync(0xFFFFFFFFu, (uint32_t)r.x, src), by0 = __shfl_sync(0xFFFFFFFFu, (uint32_t)r.y, src);
-		const uint32_t bw = __shfl_sync(0xFFFFFFFFu, (uint32_t)(r.z - r.x), src);
-		for (uint32_t k = lane; k < bn; k += 32) {
-			const uint32_t pos = bstart + k;
-			if ((int64_t)pos < capacity) { keys[pos] = (by0 + k / bw) * grid_x + (bx0 + k % bw); vals[pos] = bg; }
-		}
-	}
-}
-
-// K5: identifyTileRanges (rasterizer_impl.cu:116-138); `ranges` zero-initialised by the caller (:310)
-__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __restrict__ tile_keys, int64_t n_max,
-                                                          const unsigned long long* __restrict__ n_dev, uint2* __restrict__ ranges) {
 	const int64_t n = load_count(n_dev, n_max);
 	const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= n) return;
-	const uint32_t cur = tile_keys[idx];
-	if (idx == 0) ranges[cur].x = 0;
-	else {
-		const uint32_t prev = tile_keys[idx - 1];
-		if (cur != prev) { ranges[prev].y = (uint32_t)idx; ranges[cur].x = (uint32_t)idx; }
+	if (idx < n) {
+		const uint32_t cur = tile_keys[idx];
+		if (idx == 0) ranges[cur].x = 0;
+		else {
+			const uint32_t prev = tile_keys[idx - 1];
+			if (cur != prev) { ranges[prev].y = (uint32_t)idx; ranges[cur].x = (uint32_t)idx; }
+		}
+		if (idx == n - 1) ranges[cur].y = (uint32_t)n;
 	}
-	if (idx == n - 1) ranges[cur].y = (uint32_t)n;
+	__shared__ bool s_last;
+	__shared__ uint32_t s_cnt[128];
+	__shared__ uint32_t s_off[128];
+	__threadfence();
+	__syncthreads();
+	const int tid = threadIdx.x;
+	if (tid == 0) s_last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
+	if (tid < 128) s_cnt[tid] = 0;
+	__syncthreads();
+	if (!s_last) return;
+	__threadfence();
+	auto key_of = [](uint2 r) -> uint32_t {
+		const uint32_t len = r.y - r.x;
+		if (len == 0) return 0u;
+		const int msb = 31 - __clz(len);
+		const uint32_t frac = msb >= 2 ? (len >> (msb - 2)) & 3u : (len << (2 - msb)) & 3u;
+		return min(127u, (uint32_t)(msb + 1) * 4u + frac - 3u);
+	};
+	for (int t = tid; t < tiles; t += blockDim.x) atomicAdd(&s_cnt[key_of(__ldcg(ranges + t))], 1u);
+	__syncthreads();
+	if (tid == 0) {
+		uint32_t run = 0;
+		for (int k = 127; k >= 0; k--) { s_off[k] = run; run += s_cnt[k]; }
+	}
+	__syncthreads();
+	for (int t = tid; t < tiles; t += blockDim.x) order[atomicAdd(&s_off[key_of(__ldcg(ranges + t))], 1u)] = (uint32_t)t;
 }
 
 __global__ void __launch_bounds__(256) debug_keys_kernel(const uint32_t* __restrict__ tile_keys, const uint32_t* __restrict__ point_list,
@@ -321,12 +340,6 @@ int launch_radix_sort(uint32_t* key_a, uint32_t* key_b, uint32_t* val_a, uint32_
 	const int passes = (end_bit + 7) / 8;
 	const int items = sort_items_for(n_max);
 	const int64_t tiles = sort_tiles_for(n_max);
-	{
-		int64_t blocks = (n_max + 256 * 8 - 1) / (256 * 8);
-		if (blocks > 148 * 8) blocks = 148 * 8;
-		radix_hist_kernel<<<(unsigned)blocks, 256, 0, stream>>>(key_a, n_max, n_dev, end_bit, hist);
-		count_launch();
-	}
 	uint32_t *ki = key_a, *ko = key_b, *vi = val_a, *vo = val_b;
 	for (int p = 0; p < passes; p++) {
 		const int bits = end_bit - 8 * p < 8 ? end_bit - 8 * p : 8;
@@ -344,25 +357,23 @@ int launch_radix_sort(uint32_t* key_a, uint32_t* key_b, uint32_t* val_a, uint32_
 	return passes & 1;
 }
 
-// Depth order of the P Gaussians + instance offsets.  After this: gs.order = ids by (depth bits, id),
-// gs.offsets = inclusive scan of tiles touched in that order, hdr->num_rendered = total.
+// Depth order of the P Gaussians.  After this: gs.order = ids by (depth bits, id).
 void launch_depth_order(GeomState& gs, int P, cudaStream_t stream) {
 	if (P <= 0) return;
-	// keys: key_a (written by preprocess), values: order (identity written by preprocess); 4 passes -> result in (key_a, order)
+	// keys: key_a, values: order (identity), digit histograms gs.hist[0..3]: all written by preprocess; 4 passes -> result in (key_a, order)
 	unsigned int* tickets = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(gs.hdr) + offsetof(GeomHeader, sort_ticket));
 	launch_radix_sort(gs.key_a, gs.key_b, gs.order, gs.val_b, P, nullptr, 32, gs.hist, gs.lookback, tickets, stream);
 }
 
-void launch_offsets_scan(GeomState& gs, int P, cudaStream_t stream) {
+void launch_scan_emit(const b200gs_view_t& v, GeomState& gs, BinningState& bs, int P, int64_t capacity, cudaStream_t stream) {
 	if (P <= 0) return;
-	scan_offsets_kernel<<<(unsigned)scan_tiles_for(P), SCAN_THREADS, 0, stream>>>(gs.order, gs.rect, gs.offsets, P, gs.scan_state, gs.hdr);
-	count_launch();
-}
-
-void launch_emit(const b200gs_view_t& v, GeomState& gs, BinningState& bs, int P, int64_t capacity, cudaStream_t stream) {
-	const uint32_t gx = (v.width + TILE_X - 1) / TILE_X;
-	emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(gs.order, gs.offsets, gs.rect, P, gx, capacity, bs.key_a,
-	                                                            bs.val_a, gs.hdr);
+	const uint32_t gx = (v.width + TILE_X - 1) / TILE_X, gy = (v.height + TILE_Y - 1) / TILE_Y;
+	const int bit = (int)higher_msb(gx * gy);
+	const int64_t tiles_L = sort_tiles_for(capacity);
+	const int passes = (bit + 7) / 8;
+	const unsigned grid = (unsigned)((P + EMIT_THREADS * EMIT_ITEMS - 1) / (EMIT_THREADS * EMIT_ITEMS));
+	scan_emit_kernel<<<grid, EMIT_THREADS, 0, stream>>>(gs.order, gs.rect, P, gx, capacity, bit, bs.key_a, bs.val_a,
+		reinterpret_cast<uint32_t*>(gs.scan_state), gs.hist + 4 * 256, bs.lookback, (size_t)passes * tiles_L * 256, gs.hdr);
 	count_launch();
 }
 
@@ -377,12 +388,14 @@ void launch_tile_sort(const b200gs_view_t& v, GeomState& gs, BinningState& bs, i
 	bs.sorted_vals = where ? bs.val_b : bs.val_a;
 }
 
-void launch_tile_ranges(GeomState& gs, BinningState& bs, ImageState& is, int64_t capacity, cudaStream_t stream) {
+void launch_tile_ranges(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is, int64_t capacity, cudaStream_t stream) {
 	const unsigned long long* n_dev = &gs.hdr->num_rendered;
-	if (capacity > 0) {
-		tile_ranges_kernel<<<(unsigned)((capacity + 255) / 256), 256, 0, stream>>>(bs.sorted_keys, capacity, n_dev, is.ranges);
-		count_launch();
-	}
+	const int tiles = ((v.width + TILE_X - 1) / TILE_X) * ((v.height + TILE_Y - 1) / TILE_Y);
+	const int64_t n_max = capacity > 0 ? capacity : 0;
+	const unsigned grid = (unsigned)(n_max > 0 ? (n_max + 255) / 256 : 1);
+	unsigned int* counter = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(gs.hdr) + offsetof(GeomHeader, ranges_done));
+	tile_ranges_schedule_kernel<<<grid, 256, 0, stream>>>(bs.sorted_keys, n_max, n_dev, is.ranges, tiles, is.tile_order, counter);
+	count_launch();
 }
 
 void launch_debug_keys(const b200gs_view_t& v, GeomState& gs, BinningState& bs, uint64_t* keys_out, int64_t L,
@@ -392,4 +405,3 @@ void launch_debug_keys(const b200gs_view_t& v, GeomState& gs, BinningState& bs, 
 	debug_keys_kernel<<<(unsigned)((L + 255) / 256), 256, 0, stream>>>(bs.sorted_keys, bs.sorted_vals, gs.depths, keys_out, L);
 	count_launch();
 }
-

@@ -6,8 +6,8 @@
 // kernel's duration and `barrier` as the top stall: a tile's 8 warps wait for the slowest one twice
 // per batch, and a few deep tiles decide the kernel time.  Here the unit of work is one warp = one
 // 8x4 pixel block (8 units per tile, launched as 32-thread CTAs so the hardware CTA scheduler
-// load-balances them), units are issued heaviest tile first (longest-processing-time order from
-// tile_schedule_kernel), and nothing ever waits on another warp:
+// load-balances them), units are issued heaviest tile first (longest-processing-time order built by
+// tile_ranges_schedule_kernel in binning.cu), and nothing ever waits on another warp:
 //   * a round = 32 consecutive entries of the tile's sorted list, one per lane: the lane loads its
 //     Gaussian's 32-byte geometry (g0,g1: one sector), runs the conservative block cull for it, and
 //     only survivors fetch their payload (colour/depth/feature) and are appended to a ring in the
@@ -23,32 +23,6 @@
 #include "blend_common.cuh"
 
 namespace {
-
-// ---- heaviest-first tile order -------------------------------------------------------------------
-// key = 7 bits (position of the leading one and the next two bits of the tile's range length);
-// counting sort by descending key in one CTA.  Order inside a bucket is arbitrary (units are independent).
-__global__ void __launch_bounds__(1024) tile_schedule_kernel(const uint2* __restrict__ ranges, int tiles, uint32_t* __restrict__ order) {
-	__shared__ uint32_t s_cnt[128];
-	__shared__ uint32_t s_off[128];
-	const int tid = threadIdx.x;
-	if (tid < 128) s_cnt[tid] = 0;
-	__syncthreads();
-	auto key_of = [](uint2 r) -> uint32_t {
-		const uint32_t n = r.y - r.x;
-		if (n == 0) return 0u;
-		const int msb = 31 - __clz(n);
-		const uint32_t frac = msb >= 2 ? (n >> (msb - 2)) & 3u : (n << (2 - msb)) & 3u;
-		return min(127u, (uint32_t)(msb + 1) * 4u + frac - 3u);
-	};
-	for (int t = tid; t < tiles; t += blockDim.x) atomicAdd(&s_cnt[key_of(ranges[t])], 1u);
-	__syncthreads();
-	if (tid == 0) {
-		uint32_t run = 0;
-		for (int k = 127; k >= 0; k--) { s_off[k] = run; run += s_cnt[k]; }
-	}
-	__syncthreads();
-	for (int t = tid; t < tiles; t += blockDim.x) order[atomicAdd(&s_off[key_of(ranges[t])], 1u)] = (uint32_t)t;
-}
 
 struct Unit {
 	uint32_t tile;
@@ -437,13 +411,6 @@ void launch_blend_forward_tile(const b200gs_view_t& v, GeomState& gs, BinningSta
                                const b200gs_outputs_t& out, cudaStream_t stream);
 void launch_blend_backward_tile(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
                                 const b200gs_grad_outputs_t& gout, float* grec, cudaStream_t stream);
-
-void launch_tile_schedule(const b200gs_view_t& v, ImageState& is, cudaStream_t stream) {
-	if (use_tile_cta_path()) return;
-	const int tiles = ((v.width + TILE_X - 1) / TILE_X) * ((v.height + TILE_Y - 1) / TILE_Y);
-	tile_schedule_kernel<<<1, 1024, 0, stream>>>(is.ranges, tiles, is.tile_order);
-	count_launch();
-}
 
 void launch_blend_forward(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
                           const b200gs_outputs_t& out, cudaStream_t stream) {

@@ -24,7 +24,8 @@ struct GeomHeader {  // first 256 bytes of the geom workspace
 	unsigned int overflow;            // set when num_rendered > binning capacity
 	unsigned int scan_ticket;         // dynamic tile id allocator for the look-back scan
 	unsigned int sort_ticket[8];      // one per radix pass (4 depth passes + up to 4 tile passes)
-	unsigned int pad[52];
+	unsigned int ranges_done;         // CTAs of the tile-ranges kernel that have finished (last one builds the blend schedule)
+	unsigned int pad[51];
 };
 static_assert(sizeof(GeomHeader) == 256, "header size");
 
@@ -35,7 +36,6 @@ struct GeomState {
 	float4* rec;             // [P][4] float4 records
 	uint8_t* clamped;        // u8[P]
 	uint32_t* order;         // u32[P]  depth-sorted Gaussian ids (final sort output)
-	uint32_t* offsets;       // u32[P]  inclusive scan of tiles touched in `order` order
 	uint32_t* key_a;         // depth-sort ping-pong
 	uint32_t* key_b;
 	uint32_t* val_b;         // (val_a aliases `order`)
@@ -86,7 +86,7 @@ void count_launch(int n = 1);
 
 // ---- stage launchers (each enqueues on `stream`) ----
 void launch_preprocess_forward(const b200gs_view_t& v, const b200gs_gaussians_t& g, int32_t* radii, GeomState& gs,
-                               cudaStream_t stream);
+                               ImageState& is, cudaStream_t stream);
 void launch_preprocess_backward(const b200gs_view_t& v, const b200gs_gaussians_t& g, const int32_t* radii,
                                 GeomState& gs, const float* grec, const b200gs_grads_t& gr, cudaStream_t stream);
 void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t stream);
@@ -98,14 +98,12 @@ int launch_radix_sort(uint32_t* key_a, uint32_t* key_b, uint32_t* val_a, uint32_
                       const unsigned long long* n_dev, int end_bit, uint32_t* hist /*[passes][256]*/,
                       uint32_t* lookback, unsigned int* tickets, cudaStream_t stream);
 void launch_depth_order(GeomState& gs, int P, cudaStream_t stream);                     // stable sort of Gaussian ids by depth bits
-void launch_offsets_scan(GeomState& gs, int P, cudaStream_t stream);                    // inclusive scan of tiles touched, in depth order
-void launch_emit(const b200gs_view_t& v, GeomState& gs, BinningState& bs, int P, int64_t capacity, cudaStream_t stream);
+void launch_scan_emit(const b200gs_view_t& v, GeomState& gs, BinningState& bs, int P, int64_t capacity, cudaStream_t stream);
 void launch_tile_sort(const b200gs_view_t& v, GeomState& gs, BinningState& bs, int64_t capacity, cudaStream_t stream);
-void launch_tile_ranges(GeomState& gs, BinningState& bs, ImageState& is, int64_t capacity, cudaStream_t stream);
+void launch_tile_ranges(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is, int64_t capacity, cudaStream_t stream);
 void launch_debug_keys(const b200gs_view_t& v, GeomState& gs, BinningState& bs, uint64_t* keys_out, int64_t L,
                        cudaStream_t stream);
 
-void launch_tile_schedule(const b200gs_view_t& v, ImageState& is, cudaStream_t stream);
 void launch_blend_forward(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
                           const b200gs_outputs_t& out, cudaStream_t stream);
 void launch_blend_backward(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,

@@ -130,10 +130,16 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(
 	int W, int H, float tan_fovx, float tan_fovy, float focal_x, float focal_y, int extended, int prefiltered,
 	int32_t* __restrict__ radii, float* __restrict__ depths, ushort4* __restrict__ rects, float4* __restrict__ rec,
 	uint8_t* __restrict__ clamped, uint32_t* __restrict__ sort_keys, uint32_t* __restrict__ sort_vals,
-	GeomHeader* __restrict__ hdr)
+	uint32_t* __restrict__ depth_hist /*[4][256]*/, uint2* __restrict__ ranges, int tiles, GeomHeader* __restrict__ hdr)
 {
+	// digit histograms of the depth-sort keys (consumed by the four radix passes that follow)
+	__shared__ uint32_t s_hist[4][256];
+	for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) (&s_hist[0][0])[i] = 0;
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= P) return;
+	// tile ranges start at (0,0) for every tile (cudaMemset in the reference, rasterizer_impl.cu:310)
+	for (int t = idx; t < tiles; t += gridDim.x * blockDim.x) ranges[t] = make_uint2(0u, 0u);
+	__syncthreads();
+	if (idx < P) {
 	ViewConsts vc;
 	load_view(vc, viewmatrix, projmatrix, campos);
 	const float* v = vc.view;
@@ -246,6 +252,16 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(
 	rects[idx] = out_rect;
 	sort_keys[idx] = out_key;
 	sort_vals[idx] = (uint32_t)idx;
+	atomicAdd(&s_hist[0][out_key & 255u], 1u);
+	atomicAdd(&s_hist[1][(out_key >> 8) & 255u], 1u);
+	atomicAdd(&s_hist[2][(out_key >> 16) & 255u], 1u);
+	atomicAdd(&s_hist[3][out_key >> 24], 1u);
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) {
+		const uint32_t c = (&s_hist[0][0])[i];
+		if (c) atomicAdd(depth_hist + i, c);
+	}
 }
 
 __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means3D,
@@ -513,7 +529,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
 }  // namespace
 
 void launch_preprocess_forward(const b200gs_view_t& v, const b200gs_gaussians_t& g, int32_t* radii, GeomState& gs,
-                               cudaStream_t stream) {
+                               ImageState& is, cudaStream_t stream) {
 	const int P = g.P;
 	const float focal_y = v.height / (2.0f * v.tan_fovy);  // rasterizer_impl.cu:222-223
 	const float focal_x = v.width / (2.0f * v.tan_fovx);
@@ -521,7 +537,8 @@ void launch_preprocess_forward(const b200gs_view_t& v, const b200gs_gaussians_t&
 		P, v.sh_degree, v.sh_coeffs, g.means3D, g.scales, v.scale_modifier, g.rotations, g.opacities, g.shs,
 		g.cov3D_precomp, g.colors_precomp, g.language_feature_precomp, g.shs_language, g.confidence,
 		v.viewmatrix, v.projmatrix, v.campos, v.width, v.height, v.tan_fovx, v.tan_fovy, focal_x, focal_y,
-		v.extended, v.prefiltered, radii, gs.depths, gs.rect, gs.rec, gs.clamped, gs.key_a, gs.order, gs.hdr);
+		v.extended, v.prefiltered, radii, gs.depths, gs.rect, gs.rec, gs.clamped, gs.key_a, gs.order, gs.hist, is.ranges,
+		((v.width + TILE_X - 1) / TILE_X) * ((v.height + TILE_Y - 1) / TILE_Y), gs.hdr);
 	count_launch();
 }
 
