@@ -231,8 +231,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(
 		const uint32_t excl = lookback_exclusive(scan_state, 1, tile, total);
 		s_prefix = excl;
 		if ((int64_t)(tile + 1) * TILE >= P) {  // last tile: instance count, overflow flag
-			const unsigned long long L = (unsigned long long)excl + total;
-			hdr->num_rendered = L;
+			const unsigned long long L = (unsigned long long)excl + total;  // == hdr->num_rendered (summed by preprocess)
 			if (L > (unsigned long long)capacity) atomicOr(&hdr->overflow, 1u);
 		}
 	}

@@ -134,7 +134,9 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(
 {
 	// digit histograms of the depth-sort keys (consumed by the four radix passes that follow)
 	__shared__ uint32_t s_hist[4][256];
+	__shared__ unsigned long long s_instances;
 	for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) (&s_hist[0][0])[i] = 0;
+	if (threadIdx.x == 0) s_instances = 0ull;
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	// tile ranges start at (0,0) for every tile (cudaMemset in the reference, rasterizer_impl.cu:310)
 	for (int t = idx; t < tiles; t += gridDim.x * blockDim.x) ranges[t] = make_uint2(0u, 0u);
@@ -256,8 +258,12 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(
 	atomicAdd(&s_hist[1][(out_key >> 8) & 255u], 1u);
 	atomicAdd(&s_hist[2][(out_key >> 16) & 255u], 1u);
 	atomicAdd(&s_hist[3][out_key >> 24], 1u);
+	const unsigned long long touched = (unsigned long long)(out_rect.z - out_rect.x) * (unsigned long long)(out_rect.w - out_rect.y);
+	if (touched) atomicAdd(&s_instances, touched);
 	}
 	__syncthreads();
+	// num_rendered = total number of (Gaussian, tile) instances (what the reference reads back after its scan, rasterizer_impl.cu:281)
+	if (threadIdx.x == 0 && s_instances) atomicAdd(&hdr->num_rendered, s_instances);
 	for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) {
 		const uint32_t c = (&s_hist[0][0])[i];
 		if (c) atomicAdd(depth_hist + i, c);
