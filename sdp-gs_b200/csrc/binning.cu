@@ -72,8 +72,8 @@ template <int ITEMS>
 __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(
 	const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
 	uint32_t* __restrict__ vals_out, int64_t n_max, const unsigned long long* __restrict__ n_dev, int shift, int bits,
-	const uint32_t* __restrict__ hist /*[256] this pass*/, uint32_t* __restrict__ lookback /*[tiles][256]*/,
-	unsigned int* __restrict__ ticket)
+	const uint32_t* __restrict__ hist /*[256] this pass*/, uint32_t* __restrict__ next_hist /*[256] next pass or null*/,
+	int next_shift, int next_bits, uint32_t* __restrict__ lookback /*[tiles][256]*/, unsigned int* __restrict__ ticket)
 {
 	constexpr int TILE = SORT_THREADS * ITEMS;
 	constexpr int WARPS = SORT_THREADS / 32;
@@ -83,18 +83,23 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(
 	__shared__ uint32_t s_keys[TILE];
 	__shared__ uint32_t s_vals[TILE];
 	__shared__ uint32_t s_g[WARPS], s_l[WARPS];
+	__shared__ uint32_t s_next[256];
 	__shared__ uint32_t s_tile;
+	__shared__ int s_trivial;
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-	for (int i = tid; i < WARPS * 256; i += SORT_THREADS) (&s_warp_hist[0][0])[i] = 0;
-	__syncthreads();
-	const uint32_t tile = s_tile;
 	const int64_t n = load_count(n_dev, n_max);
+	if (tid == 0) { s_tile = atomicAdd(ticket, 1u); s_trivial = 0; }
+	for (int i = tid; i < WARPS * 256; i += SORT_THREADS) (&s_warp_hist[0][0])[i] = 0;
+	s_next[tid] = 0;
+	__syncthreads();
+	if ((int64_t)hist[tid] == n && n > 0) s_trivial = 1;  // every key has the same digit: the pass is the identity permutation
+	const uint32_t tile = s_tile;
 	const int64_t tile_base = (int64_t)tile * TILE;
 	if (tile_base >= n) return;
 	const int tile_n = (int)min((int64_t)TILE, n - tile_base);
 	const uint32_t dmask = (1u << bits) - 1;
+	const uint32_t nmask = (1u << next_bits) - 1;
 
 	// 1. load (warp-striped: warp w owns a contiguous 32*ITEMS chunk) and rank within the warp
 	uint32_t key[ITEMS], val[ITEMS], rnk[ITEMS];
@@ -105,6 +110,17 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(
 		const bool valid = li < tile_n;
 		key[j] = valid ? keys_in[tile_base + li] : 0xFFFFFFFFu;
 		val[j] = valid ? vals_in[tile_base + li] : 0u;
+		if (valid && next_hist != nullptr) atomicAdd(&s_next[(key[j] >> next_shift) & nmask], 1u);
+	}
+	__syncthreads();
+	if (next_hist != nullptr && s_next[tid]) atomicAdd(next_hist + tid, s_next[tid]);
+	if (s_trivial) {
+#pragma unroll
+		for (int j = 0; j < ITEMS; j++) {
+			const int li = warp_base + j * 32 + lane;
+			if (li < tile_n) { keys_out[tile_base + li] = key[j]; vals_out[tile_base + li] = val[j]; }
+		}
+		return;
 	}
 #pragma unroll
 	for (int j = 0; j < ITEMS; j++) {
@@ -177,7 +193,7 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(
 // half of the reference's key is implied by the emission order, so only the tile id is written as sort key.
 // Also: digit histograms of the tile ids for the tile sort, and the zeroing of its look-back words.
 constexpr int EMIT_THREADS = 256;
-constexpr int EMIT_ITEMS = 4;
+constexpr int EMIT_ITEMS = 1;
 constexpr uint32_t EMIT_SMALL = 12;
 
 __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(
@@ -187,14 +203,13 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(
 	GeomHeader* __restrict__ hdr)
 {
 	constexpr int TILE = EMIT_THREADS * EMIT_ITEMS;
-	__shared__ uint32_t s_hist[4][256];
+	__shared__ uint32_t s_hist[256];  // first digit of the tile ids; later digits are histogrammed by the pass before them
 	__shared__ uint32_t s_warp[EMIT_THREADS / 32];
 	__shared__ uint32_t s_prefix;
 	__shared__ uint32_t s_tile;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int passes = (tile_bits + 7) / 8;
 	if (tid == 0) s_tile = atomicAdd(&hdr->scan_ticket, 1u);
-	for (int i = tid; i < 4 * 256; i += EMIT_THREADS) (&s_hist[0][0])[i] = 0;
+	s_hist[tid] = 0;
 	// zero the tile sort's look-back words (they are first read by the next kernel)
 	for (size_t i = (size_t)blockIdx.x * EMIT_THREADS + tid; i < zero_count; i += (size_t)gridDim.x * EMIT_THREADS) zero_words[i] = 0;
 	__syncthreads();
@@ -243,8 +258,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(
 		if ((int64_t)pos < capacity) {
 			keys[pos] = key;
 			vals[pos] = val;
-			atomicAdd(&s_hist[0][key & m0], 1u);
-			for (int p = 1; p < passes; p++) atomicAdd(&s_hist[p][(key >> (8 * p)) & ((1u << min(8, tile_bits - 8 * p)) - 1u)], 1u);
+			atomicAdd(&s_hist[key & m0], 1u);
 		}
 	};
 #pragma unroll
@@ -270,10 +284,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(
 		start += n[k];
 	}
 	__syncthreads();
-	for (int i = tid; i < passes * 256; i += EMIT_THREADS) {
-		const uint32_t c = (&s_hist[0][0])[i];
-		if (c) atomicAdd(tile_hist + i, c);
-	}
+	if (s_hist[tid]) atomicAdd(tile_hist + tid, s_hist[tid]);
 }
 
 // K5: identifyTileRanges (rasterizer_impl.cu:116-138; `ranges` zero-initialised by the preprocess kernel, :310),
@@ -285,8 +296,7 @@ __global__ void __launch_bounds__(256) tile_ranges_schedule_kernel(
 	uint2* __restrict__ ranges, int tiles, uint32_t* __restrict__ order, unsigned int* __restrict__ done_counter)
 {
 	const int64_t n = load_count(n_dev, n_max);
-	const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx < n) {
+	for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
 		const uint32_t cur = tile_keys[idx];
 		if (idx == 0) ranges[cur].x = 0;
 		else {
@@ -342,13 +352,16 @@ int launch_radix_sort(uint32_t* key_a, uint32_t* key_b, uint32_t* val_a, uint32_
 	uint32_t *ki = key_a, *ko = key_b, *vi = val_a, *vo = val_b;
 	for (int p = 0; p < passes; p++) {
 		const int bits = end_bit - 8 * p < 8 ? end_bit - 8 * p : 8;
+		const bool more = p + 1 < passes;
+		const int nbits = more ? (end_bit - 8 * (p + 1) < 8 ? end_bit - 8 * (p + 1) : 8) : 1;
+		uint32_t* nh = more ? hist + 256 * (p + 1) : nullptr;  // histogram of the next pass's digit, taken while this pass reads the keys
 		uint32_t* lb = lookback + (size_t)p * tiles * 256;
 		if (items == SORT_ITEMS_SMALL)
 			onesweep_pass_kernel<SORT_ITEMS_SMALL><<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(
-				ki, vi, ko, vo, n_max, n_dev, 8 * p, bits, hist + 256 * p, lb, tickets + p);
+				ki, vi, ko, vo, n_max, n_dev, 8 * p, bits, hist + 256 * p, nh, 8 * (p + 1), nbits, lb, tickets + p);
 		else
 			onesweep_pass_kernel<SORT_ITEMS_LARGE><<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(
-				ki, vi, ko, vo, n_max, n_dev, 8 * p, bits, hist + 256 * p, lb, tickets + p);
+				ki, vi, ko, vo, n_max, n_dev, 8 * p, bits, hist + 256 * p, nh, 8 * (p + 1), nbits, lb, tickets + p);
 		count_launch();
 		uint32_t* t = ki; ki = ko; ko = t;
 		t = vi; vi = vo; vo = t;
@@ -391,7 +404,8 @@ void launch_tile_ranges(const b200gs_view_t& v, GeomState& gs, BinningState& bs,
 	const unsigned long long* n_dev = &gs.hdr->num_rendered;
 	const int tiles = ((v.width + TILE_X - 1) / TILE_X) * ((v.height + TILE_Y - 1) / TILE_Y);
 	const int64_t n_max = capacity > 0 ? capacity : 0;
-	const unsigned grid = (unsigned)(n_max > 0 ? (n_max + 255) / 256 : 1);
+	// few CTAs (grid-stride): every CTA ends with one atomic on the same counter
+	const unsigned grid = (unsigned)(n_max > 0 ? (n_max + 255) / 256 < 148 * 4 ? (n_max + 255) / 256 : 148 * 4 : 1);
 	unsigned int* counter = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(gs.hdr) + offsetof(GeomHeader, ranges_done));
 	tile_ranges_schedule_kernel<<<grid, 256, 0, stream>>>(bs.sorted_keys, n_max, n_dev, is.ranges, tiles, is.tile_order, counter);
 	count_launch();

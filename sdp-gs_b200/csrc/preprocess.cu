@@ -130,12 +130,12 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(
 	int W, int H, float tan_fovx, float tan_fovy, float focal_x, float focal_y, int extended, int prefiltered,
 	int32_t* __restrict__ radii, float* __restrict__ depths, ushort4* __restrict__ rects, float4* __restrict__ rec,
 	uint8_t* __restrict__ clamped, uint32_t* __restrict__ sort_keys, uint32_t* __restrict__ sort_vals,
-	uint32_t* __restrict__ depth_hist /*[4][256]*/, uint2* __restrict__ ranges, int tiles, GeomHeader* __restrict__ hdr)
+	uint32_t* __restrict__ depth_hist /*[256]: first digit; later digits are histogrammed by the pass before them*/, uint2* __restrict__ ranges, int tiles, GeomHeader* __restrict__ hdr)
 {
 	// digit histograms of the depth-sort keys (consumed by the four radix passes that follow)
-	__shared__ uint32_t s_hist[4][256];
+	__shared__ uint32_t s_hist[256];
 	__shared__ unsigned long long s_instances;
-	for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) (&s_hist[0][0])[i] = 0;
+	for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
 	if (threadIdx.x == 0) s_instances = 0ull;
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	// tile ranges start at (0,0) for every tile (cudaMemset in the reference, rasterizer_impl.cu:310)
@@ -254,19 +254,15 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(
 	rects[idx] = out_rect;
 	sort_keys[idx] = out_key;
 	sort_vals[idx] = (uint32_t)idx;
-	atomicAdd(&s_hist[0][out_key & 255u], 1u);
-	atomicAdd(&s_hist[1][(out_key >> 8) & 255u], 1u);
-	atomicAdd(&s_hist[2][(out_key >> 16) & 255u], 1u);
-	atomicAdd(&s_hist[3][out_key >> 24], 1u);
+	atomicAdd(&s_hist[out_key & 255u], 1u);
 	const unsigned long long touched = (unsigned long long)(out_rect.z - out_rect.x) * (unsigned long long)(out_rect.w - out_rect.y);
 	if (touched) atomicAdd(&s_instances, touched);
 	}
 	__syncthreads();
 	// num_rendered = total number of (Gaussian, tile) instances (what the reference reads back after its scan, rasterizer_impl.cu:281)
 	if (threadIdx.x == 0 && s_instances) atomicAdd(&hdr->num_rendered, s_instances);
-	for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) {
-		const uint32_t c = (&s_hist[0][0])[i];
-		if (c) atomicAdd(depth_hist + i, c);
+	for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+		if (s_hist[i]) atomicAdd(depth_hist + i, s_hist[i]);
 	}
 }
 
