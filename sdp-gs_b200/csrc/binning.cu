@@ -192,8 +192,8 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(
 // look-back, and duplicateWithKeys (rasterizer_impl.cu:70-111) straight from the scanned offsets.  The depth
 // half of the reference's key is implied by the emission order, so only the tile id is written as sort key.
 // Also: digit histograms of the tile ids for the tile sort, and the zeroing of its look-back words.
-constexpr int EMIT_THREADS = 256;
-constexpr int EMIT_ITEMS = 1;
+constexpr int EMIT_THREADS = SCAN_THREADS;
+constexpr int EMIT_ITEMS = SCAN_ITEMS;
 constexpr uint32_t EMIT_SMALL = 12;
 
 __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(
