@@ -7,6 +7,7 @@
 // round-to-nearest intrinsics in the order the reference's sm_100a build executes them (read off
 // its SASS: cicc *and* ptxas contract mul+add into fma there, e.g. det = fma(a, c, -(b*b))).
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace {
 
@@ -121,7 +122,30 @@ __device__ __forceinline__ void sh_to_rgb(int deg, const float* __restrict__ sh,
 	}
 }
 
-__global__ void __launch_bounds__(256) preprocess_forward_kernel(
+// One CTA handles PRE_THREADS consecutive Gaussians.  Their attribute arrays are array-of-structs with odd strides
+// (12, 16, 24, 12*M bytes), which makes per-thread global loads touch ~20 sectors per request (ncu, round 1).  The
+// CTA's slice of every array is contiguous in memory, so it is brought into shared memory whole: by the TMA bulk-copy
+// engine (cp.async.bulk + mbarrier) when the slice is a full, 16-byte aligned tile, by coalesced loads otherwise.
+constexpr int PRE_THREADS = 128;
+
+struct Stage {
+	uint64_t* bar;
+	uint32_t tx;
+	bool tma;
+	int cnt;
+	int tid;
+	__device__ __forceinline__ void load(float* dst, const float* src, int floats_per_item, size_t base) {
+		if (src == nullptr) return;
+		const float* g = src + base * floats_per_item;
+		if (tma) {
+			if (tid == 0) { const uint32_t bytes = (uint32_t)(PRE_THREADS * floats_per_item * 4); tma_load_1d(dst, g, bytes, bar); }
+		} else {
+			for (int i = tid; i < cnt * floats_per_item; i += PRE_THREADS) dst[i] = g[i];
+		}
+	}
+};
+
+__global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(
 	int P, int D, int M, const float* __restrict__ means3D, const float* __restrict__ scales, float scale_modifier,
 	const float* __restrict__ rotations, const float* __restrict__ opacities, const float* __restrict__ shs,
 	const float* __restrict__ cov3D_precomp, const float* __restrict__ colors_precomp,
@@ -130,17 +154,53 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(
 	int W, int H, float tan_fovx, float tan_fovy, float focal_x, float focal_y, int extended, int prefiltered,
 	int32_t* __restrict__ radii, float* __restrict__ depths, ushort4* __restrict__ rects, float4* __restrict__ rec,
 	uint8_t* __restrict__ clamped, uint32_t* __restrict__ sort_keys, uint32_t* __restrict__ sort_vals,
-	uint32_t* __restrict__ depth_hist /*[256]: first digit; later digits are histogrammed by the pass before them*/, uint2* __restrict__ ranges, int tiles, GeomHeader* __restrict__ hdr)
+	uint32_t* __restrict__ depth_hist /*[256]: first digit; later digits are histogrammed by the pass before them*/, uint2* __restrict__ ranges, int tiles, GeomHeader* __restrict__ hdr,
+	int tma_ok)
 {
 	// digit histograms of the depth-sort keys (consumed by the four radix passes that follow)
 	__shared__ uint32_t s_hist[256];
 	__shared__ unsigned long long s_instances;
+	__shared__ __align__(128) float s_sh[PRE_THREADS * 48];     // SH coefficients (M <= 16) or precomputed colours
+	__shared__ __align__(16) float s_means[PRE_THREADS * 3];
+	__shared__ __align__(16) float s_geo[PRE_THREADS * 7];      // scales [0,3T) + rotations [3T,7T), or cov3D_precomp [0,6T)
+	__shared__ __align__(16) float s_opac[PRE_THREADS];
+	__shared__ __align__(16) float s_conf[PRE_THREADS];
+	__shared__ __align__(16) float s_feat[PRE_THREADS * 3];     // language_feature_precomp or shs_language
+	__shared__ __align__(128) float4 s_rec[PRE_THREADS * 4];    // outgoing splat records
+	__shared__ __align__(8) uint64_t s_bar;
+	const int li = threadIdx.x;
+	const size_t base = (size_t)blockIdx.x * PRE_THREADS;
+	const int cnt = (int)min((size_t)PRE_THREADS, (size_t)P - base);
+	const bool sh_staged = shs != nullptr && M <= 16;
+	Stage st;
+	st.bar = &s_bar; st.tma = tma_ok && cnt == PRE_THREADS; st.cnt = cnt; st.tid = li;
+	if (li == 0 && st.tma) mbar_init(&s_bar, 1);
 	for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
 	if (threadIdx.x == 0) s_instances = 0ull;
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	// tile ranges start at (0,0) for every tile (cudaMemset in the reference, rasterizer_impl.cu:310)
 	for (int t = idx; t < tiles; t += gridDim.x * blockDim.x) ranges[t] = make_uint2(0u, 0u);
 	__syncthreads();
+	if (li == 0 && st.tma) {
+		uint32_t tx = PRE_THREADS * 4 * (3 + 1);
+		tx += (cov3D_precomp != nullptr) ? PRE_THREADS * 4 * 6 : PRE_THREADS * 4 * 7;
+		if (sh_staged) tx += PRE_THREADS * 4 * 3 * M;
+		if (colors_precomp != nullptr) tx += PRE_THREADS * 4 * 3;
+		if (confidence != nullptr) tx += PRE_THREADS * 4;
+		if (extended && (feat_precomp != nullptr || shs_language != nullptr)) tx += PRE_THREADS * 4 * 3;
+		mbar_arrive_expect_tx(&s_bar, tx);
+	}
+	st.load(s_means, means3D, 3, base);
+	st.load(s_opac, opacities, 1, base);
+	if (cov3D_precomp != nullptr) st.load(s_geo, cov3D_precomp, 6, base);
+	else { st.load(s_geo, scales, 3, base); st.load(s_geo + 3 * PRE_THREADS, rotations, 4, base); }
+	if (sh_staged) st.load(s_sh, shs, 3 * M, base);
+	if (colors_precomp != nullptr) st.load(s_sh, colors_precomp, 3, base);
+	if (confidence != nullptr) st.load(s_conf, confidence, 1, base);
+	if (extended) st.load(s_feat, feat_precomp != nullptr ? feat_precomp : shs_language, 3, base);
+	if (st.tma) mbar_wait(&s_bar, 0);
+	else __syncthreads();
+	float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0, r3 = r0;
 	if (idx < P) {
 	ViewConsts vc;
 	load_view(vc, viewmatrix, projmatrix, campos);
@@ -151,7 +211,7 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(
 	ushort4 out_rect = make_ushort4(0, 0, 0, 0);
 	uint32_t out_key = 0xFFFFFFFFu;
 
-	const float x = __ldg(means3D + 3 * idx), y = __ldg(means3D + 3 * idx + 1), z = __ldg(means3D + 3 * idx + 2);
+	const float x = s_means[3 * li], y = s_means[3 * li + 1], z = s_means[3 * li + 2];
 	const float pz = xform_row(v, 2, x, y, z);
 	bool alive = !(pz <= 0.2f);  // in_frustum, auxiliary.h:154
 	if (!alive && prefiltered) atomicOr(&hdr->overflow, 2u);  // reference: printf + __trap (auxiliary.h:156-160)
@@ -165,11 +225,10 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(
 		float c3[6];
 		if (cov3D_precomp != nullptr) {
 #pragma unroll
-			for (int i = 0; i < 6; i++) c3[i] = __ldg(cov3D_precomp + 6 * idx + i);
+			for (int i = 0; i < 6; i++) c3[i] = s_geo[6 * li + i];
 		} else {
-			const float4 q = __ldg(reinterpret_cast<const float4*>(rotations) + idx);
-			cov3d_pinned(__ldg(scales + 3 * idx), __ldg(scales + 3 * idx + 1), __ldg(scales + 3 * idx + 2),
-			             scale_modifier, q, c3);
+			const float4 q = reinterpret_cast<const float4*>(s_geo + 3 * PRE_THREADS)[li];
+			cov3d_pinned(s_geo[3 * li], s_geo[3 * li + 1], s_geo[3 * li + 2], scale_modifier, q, c3);
 		}
 		// computeCov2D
 		const float tx = xform_row(v, 0, x, y, z), ty = xform_row(v, 1, x, y, z), tz = pz;
@@ -214,34 +273,31 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(
 				float rgb[3];
 				unsigned clamp_bits = 0;
 				if (colors_precomp != nullptr) {
-					rgb[0] = __ldg(colors_precomp + 3 * idx); rgb[1] = __ldg(colors_precomp + 3 * idx + 1);
-					rgb[2] = __ldg(colors_precomp + 3 * idx + 2);
+					rgb[0] = s_sh[3 * li]; rgb[1] = s_sh[3 * li + 1]; rgb[2] = s_sh[3 * li + 2];
 				} else {
-					sh_to_rgb(D, shs + (size_t)idx * M * 3, __fsub_rn(x, vc.campos[0]), __fsub_rn(y, vc.campos[1]),
+					sh_to_rgb(D, sh_staged ? s_sh + li * M * 3 : shs + (size_t)idx * M * 3, __fsub_rn(x, vc.campos[0]), __fsub_rn(y, vc.campos[1]),
 					          __fsub_rn(z, vc.campos[2]), rgb, clamp_bits);
 				}
 				float f[3] = {rgb[0], rgb[1], rgb[2]};  // include_feature=False: feature aliases colour
 				if (extended) {
 					if (feat_precomp != nullptr) {
-						f[0] = __ldg(feat_precomp + 3 * idx); f[1] = __ldg(feat_precomp + 3 * idx + 1);
-						f[2] = __ldg(feat_precomp + 3 * idx + 2);
+						f[0] = s_feat[3 * li]; f[1] = s_feat[3 * li + 1]; f[2] = s_feat[3 * li + 2];
 					} else if (shs_language != nullptr) {  // gaussian_renderer/__init__.py:283-287
-						const float v0 = kSH_C0 * __ldg(shs_language + 3 * idx), v1 = kSH_C0 * __ldg(shs_language + 3 * idx + 1);
-						const float v2 = kSH_C0 * __ldg(shs_language + 3 * idx + 2);
+						const float v0 = kSH_C0 * s_feat[3 * li], v1 = kSH_C0 * s_feat[3 * li + 1];
+						const float v2 = kSH_C0 * s_feat[3 * li + 2];
 						const float inv = 1.0f / (sqrtf(v0 * v0 + v1 * v1 + v2 * v2) + 1e-9f);
 						f[0] = v0 * inv; f[1] = v1 * inv; f[2] = v2 * inv;
 					}
 				}
-				float o = __ldg(opacities + idx);
-				if (confidence != nullptr) o *= __ldg(confidence + idx);
+				float o = s_opac[li];
+				if (confidence != nullptr) o *= s_conf[li];
 				const float ca = __fmul_rn(c, det_inv), cb = __fmul_rn(b, -det_inv), cc = __fmul_rn(a, det_inv);
 				// warp-level cull helpers for the blend kernels (conservative, see blend.cu)
 				const float thr = 2.0f * logf(255.0f * o);
-				float4* rp = rec + 4 * (size_t)idx;
-				rp[0] = make_float4(pxi, pyi, ca, cb);
-				rp[1] = make_float4(cc, o, thr, -cb / cc);
-				rp[2] = make_float4(rgb[0], rgb[1], rgb[2], pz);
-				rp[3] = make_float4(f[0], f[1], f[2], 0.f);
+				r0 = make_float4(pxi, pyi, ca, cb);
+				r1 = make_float4(cc, o, thr, -cb / cc);
+				r2 = make_float4(rgb[0], rgb[1], rgb[2], pz);
+				r3 = make_float4(f[0], f[1], f[2], 0.f);
 				clamped[idx] = (uint8_t)clamp_bits;
 				depths[idx] = pz;
 				out_radius = irad;
@@ -258,7 +314,15 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(
 	const unsigned long long touched = (unsigned long long)(out_rect.z - out_rect.x) * (unsigned long long)(out_rect.w - out_rect.y);
 	if (touched) atomicAdd(&s_instances, touched);
 	}
+	// splat records leave the CTA as one contiguous bulk store
+	s_rec[4 * li] = r0; s_rec[4 * li + 1] = r1; s_rec[4 * li + 2] = r2; s_rec[4 * li + 3] = r3;
+	tma_store_fence();
 	__syncthreads();
+	if (li == 0) {
+		tma_store_1d(rec + 4 * base, s_rec, (uint32_t)cnt * 64u);
+		tma_store_commit();
+		tma_store_wait_read();
+	}
 	// num_rendered = total number of (Gaussian, tile) instances (what the reference reads back after its scan, rasterizer_impl.cu:281)
 	if (threadIdx.x == 0 && s_instances) atomicAdd(&hdr->num_rendered, s_instances);
 	for (int i = threadIdx.x; i < 256; i += blockDim.x) {
@@ -286,7 +350,7 @@ __device__ __forceinline__ void store3(float* p, size_t i, float a, float b, flo
 	if (p) { p[3 * i] = a; p[3 * i + 1] = b; p[3 * i + 2] = c; }
 }
 
-__global__ void __launch_bounds__(256) preprocess_backward_kernel(
+__global__ void __launch_bounds__(PRE_THREADS) preprocess_backward_kernel(
 	int P, int D, int M, const float* __restrict__ means3D, const int32_t* __restrict__ radii,
 	const float* __restrict__ shs, const uint8_t* __restrict__ clamped, const float* __restrict__ scales,
 	const float* __restrict__ rotations, float scale_modifier, const float* __restrict__ cov3D_precomp,
@@ -297,47 +361,80 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
 	float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dshs,
 	float* __restrict__ dL_dcolors, float* __restrict__ dL_dopac, float* __restrict__ dL_dscales,
 	float* __restrict__ dL_drots, float* __restrict__ dL_dcov3D, float* __restrict__ dL_dfeat,
-	float* __restrict__ dL_dshs_lang)
+	float* __restrict__ dL_dshs_lang, int tma_ok)
 {
-	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= P) return;
-	if (!(radii[idx] > 0)) {
-		store3(dL_dmeans3D, idx, 0.f, 0.f, 0.f);
-		store3(dL_dmeans2D, idx, 0.f, 0.f, 0.f);
-		store3(dL_dcolors, idx, 0.f, 0.f, 0.f);
-		store3(dL_dscales, idx, 0.f, 0.f, 0.f);
-		store3(dL_dfeat, idx, 0.f, 0.f, 0.f);
-		store3(dL_dshs_lang, idx, 0.f, 0.f, 0.f);
-		if (dL_dopac) dL_dopac[idx] = 0.f;
-		if (dL_drots) reinterpret_cast<float4*>(dL_drots)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-		if (dL_dcov3D) for (int i = 0; i < 6; i++) dL_dcov3D[6 * (size_t)idx + i] = 0.f;
-		if (dL_dshs) for (int i = 0; i < 3 * M; i++) dL_dshs[(size_t)idx * 3 * M + i] = 0.f;
-		return;
+	// inputs staged as in the forward; the same buffers are reused for the outgoing gradients (a thread only ever
+	// touches its own row), which leave as contiguous bulk stores instead of 12/24/192-byte strided scalar stores
+	__shared__ __align__(128) float s_sh[PRE_THREADS * 48];     // SH in -> dL/dSH out
+	__shared__ __align__(128) float4 s_grec[PRE_THREADS * 4];
+	__shared__ __align__(16) float s_means[PRE_THREADS * 3];    // means in -> dL/dmeans3D out
+	__shared__ __align__(16) float s_geo[PRE_THREADS * 7];      // scales+rotations / cov3D in -> dL/dscales / dL/dcov3D out
+	__shared__ __align__(16) float s_feat[PRE_THREADS * 3];     // feature / language SH in -> their gradient out
+	__shared__ __align__(16) float s_conf[PRE_THREADS];
+	__shared__ __align__(16) float s_o2[PRE_THREADS * 3];       // dL/dmeans2D out
+	__shared__ __align__(16) float s_oc[PRE_THREADS * 3];       // dL/dcolors out
+	__shared__ __align__(8) uint64_t s_bar;
+	const int li = threadIdx.x;
+	const size_t base = (size_t)blockIdx.x * PRE_THREADS;
+	const int cnt = (int)min((size_t)PRE_THREADS, (size_t)P - base);
+	const bool sh_staged = shs != nullptr && M <= 16;
+	const bool full = tma_ok && cnt == PRE_THREADS;
+	Stage st;
+	st.bar = &s_bar; st.tma = full; st.cnt = cnt; st.tid = li;
+	if (li == 0 && full) mbar_init(&s_bar, 1);
+	__syncthreads();
+	if (li == 0 && full) {
+		uint32_t tx = PRE_THREADS * 4 * (16 + 3);
+		tx += (cov3D_precomp != nullptr) ? PRE_THREADS * 4 * 6 : PRE_THREADS * 4 * 7;
+		if (sh_staged) tx += PRE_THREADS * 4 * 3 * M;
+		if (confidence != nullptr) tx += PRE_THREADS * 4;
+		if (extended && shs_language != nullptr && feat_precomp == nullptr) tx += PRE_THREADS * 4 * 3;
+		mbar_arrive_expect_tx(&s_bar, tx);
 	}
+	st.load(reinterpret_cast<float*>(s_grec), reinterpret_cast<const float*>(grec), 16, base);
+	st.load(s_means, means3D, 3, base);
+	if (cov3D_precomp != nullptr) st.load(s_geo, cov3D_precomp, 6, base);
+	else { st.load(s_geo, scales, 3, base); st.load(s_geo + 3 * PRE_THREADS, rotations, 4, base); }
+	if (sh_staged) st.load(s_sh, shs, 3 * M, base);
+	if (confidence != nullptr) st.load(s_conf, confidence, 1, base);
+	if (extended && shs_language != nullptr && feat_precomp == nullptr) st.load(s_feat, shs_language, 3, base);
+	if (full) mbar_wait(&s_bar, 0);
+	else __syncthreads();
+
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	// per-Gaussian results (zeros for Gaussians that were not rendered: the reference's torch::zeros)
+	float o_mean[3] = {0.f, 0.f, 0.f}, o_m2[2] = {0.f, 0.f}, o_col[3] = {0.f, 0.f, 0.f}, o_sc[3] = {0.f, 0.f, 0.f};
+	float o_feat[3] = {0.f, 0.f, 0.f}, o_shl[3] = {0.f, 0.f, 0.f}, o_cov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+	float o_op = 0.f;
+	float4 o_rot = make_float4(0.f, 0.f, 0.f, 0.f);
+	float shw[16];  // dL/dSH[k][c] = shw[k] * dRGB[c]
+#pragma unroll
+	for (int k = 0; k < 16; k++) shw[k] = 0.f;
+	float dRGB[3] = {0.f, 0.f, 0.f};
+	if (idx < P && radii[idx] > 0) {
 	ViewConsts vc;
 	load_view(vc, viewmatrix, projmatrix, campos);
 	const float* vm = vc.view;
 	const float* proj = vc.proj;
 
-	const float4 g0 = grec[4 * (size_t)idx], g1 = grec[4 * (size_t)idx + 1], g2 = grec[4 * (size_t)idx + 2],
-	             g3 = grec[4 * (size_t)idx + 3];
+	const float4 g0 = s_grec[4 * li], g1 = s_grec[4 * li + 1], g2 = s_grec[4 * li + 2], g3 = s_grec[4 * li + 3];
 	const float dm2x = g0.x, dm2y = g0.y, dca = g0.z, dcb = g0.w, dcc = g1.x;
 	float dop = g1.y;
-	float dRGB[3] = {g1.z, g1.w, g2.x};
+	dRGB[0] = g1.z; dRGB[1] = g1.w; dRGB[2] = g2.x;
 	const float dz = g2.y;
 	const float df[3] = {g2.z, g2.w, g3.x};
 
-	const float mx = means3D[3 * idx], my = means3D[3 * idx + 1], mz = means3D[3 * idx + 2];
+	const float mx = s_means[3 * li], my = s_means[3 * li + 1], mz = s_means[3 * li + 2];
 
 	// cov3D (recomputed; the reference stores it in geomState.cov3D)
 	float c3[6];
 	float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
 	float s3[3] = {0.f, 0.f, 0.f};
 	if (cov3D_precomp != nullptr) {
-		for (int i = 0; i < 6; i++) c3[i] = cov3D_precomp[6 * (size_t)idx + i];
+		for (int i = 0; i < 6; i++) c3[i] = s_geo[6 * li + i];
 	} else {
-		q = reinterpret_cast<const float4*>(rotations)[idx];
-		s3[0] = scales[3 * idx]; s3[1] = scales[3 * idx + 1]; s3[2] = scales[3 * idx + 2];
+		q = reinterpret_cast<const float4*>(s_geo + 3 * PRE_THREADS)[li];
+		s3[0] = s_geo[3 * li]; s3[1] = s_geo[3 * li + 1]; s3[2] = s_geo[3 * li + 2];
 		cov3d_pinned(s3[0], s3[1], s3[2], scale_modifier, q, c3);
 	}
 
@@ -408,38 +505,30 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
 	// ---- feature head ----
 	if (extended) {
 		if (feat_precomp != nullptr) {
-			store3(dL_dfeat, idx, df[0], df[1], df[2]);
-			store3(dL_dshs_lang, idx, 0.f, 0.f, 0.f);
+			o_feat[0] = df[0]; o_feat[1] = df[1]; o_feat[2] = df[2];
 		} else if (shs_language != nullptr) {
-			const float v0 = kSH_C0 * shs_language[3 * idx], v1 = kSH_C0 * shs_language[3 * idx + 1], v2 = kSH_C0 * shs_language[3 * idx + 2];
+			const float v0 = kSH_C0 * s_feat[3 * li], v1 = kSH_C0 * s_feat[3 * li + 1], v2 = kSH_C0 * s_feat[3 * li + 2];
 			const float n = sqrtf(v0 * v0 + v1 * v1 + v2 * v2), ne = n + 1e-9f;
 			const float vd = v0 * df[0] + v1 * df[1] + v2 * df[2];
 			const float k = (n > 0.f) ? vd / (n * ne * ne) : 0.f;
-			store3(dL_dshs_lang, idx, kSH_C0 * (df[0] / ne - v0 * k), kSH_C0 * (df[1] / ne - v1 * k), kSH_C0 * (df[2] / ne - v2 * k));
-			store3(dL_dfeat, idx, 0.f, 0.f, 0.f);
+			o_shl[0] = kSH_C0 * (df[0] / ne - v0 * k); o_shl[1] = kSH_C0 * (df[1] / ne - v1 * k); o_shl[2] = kSH_C0 * (df[2] / ne - v2 * k);
 		} else {  // feature channels alias the colours
 			dRGB[0] += df[0]; dRGB[1] += df[1]; dRGB[2] += df[2];
-			store3(dL_dfeat, idx, 0.f, 0.f, 0.f);
-			store3(dL_dshs_lang, idx, 0.f, 0.f, 0.f);
 		}
 	}
 
 	// ---- colours: either straight out, or SH backward ----
 	if (shs == nullptr) {
-		store3(dL_dcolors, idx, dRGB[0], dRGB[1], dRGB[2]);
+		o_col[0] = dRGB[0]; o_col[1] = dRGB[1]; o_col[2] = dRGB[2];
 	} else {
-		store3(dL_dcolors, idx, 0.f, 0.f, 0.f);
 		const unsigned cl = clamped[idx];
 		dRGB[0] *= (cl & 1u) ? 0.f : 1.f; dRGB[1] *= (cl & 2u) ? 0.f : 1.f; dRGB[2] *= (cl & 4u) ? 0.f : 1.f;
 		const float dox = mx - vc.campos[0], doy = my - vc.campos[1], doz = mz - vc.campos[2];
 		const float ilen = 1.0f / sqrtf(dox * dox + doy * doy + doz * doz);
 		const float x = dox * ilen, y = doy * ilen, z = doz * ilen;
-		const float* sh = shs + (size_t)idx * M * 3;
-		float* dsh = dL_dshs + (size_t)idx * M * 3;
+		const float* sh = sh_staged ? s_sh + li * M * 3 : shs + (size_t)idx * M * 3;
 		float ddir[3] = {0.f, 0.f, 0.f};  // dL/ddir
-		auto wr = [&](int k, float w) {
-			if (dL_dshs) { dsh[3 * k] = w * dRGB[0]; dsh[3 * k + 1] = w * dRGB[1]; dsh[3 * k + 2] = w * dRGB[2]; }
-		};
+		auto wr = [&](int k, float w) { shw[k] = w; };  // the row is written after every read of `sh` (same buffer)
 		auto shdot = [&](int k) { return sh[3 * k] * dRGB[0] + sh[3 * k + 1] * dRGB[1] + sh[3 * k + 2] * dRGB[2]; };
 		wr(0, kSH_C0);
 		int written = 1;
@@ -476,7 +565,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
 				}
 			}
 		}
-		if (dL_dshs) for (int i = 3 * written; i < 3 * M; i++) dsh[i] = 0.f;
+		(void)written;
 		// dnormvdv (auxiliary.h:107-117)
 		const float sum2 = dox * dox + doy * doy + doz * doz;
 		const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
@@ -485,18 +574,16 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
 		dmean[2] += (-dox * doz * ddir[0] - doy * doz * ddir[1] + (sum2 - doz * doz) * ddir[2]) * invsum32;
 	}
 
-	store3(dL_dmeans3D, idx, dmean[0], dmean[1], dmean[2]);
-	store3(dL_dmeans2D, idx, dm2x, dm2y, 0.f);
-	if (confidence != nullptr) dop *= confidence[idx];
-	if (dL_dopac) dL_dopac[idx] = dop;
+	o_mean[0] = dmean[0]; o_mean[1] = dmean[1]; o_mean[2] = dmean[2];
+	o_m2[0] = dm2x; o_m2[1] = dm2y;
+	if (confidence != nullptr) dop *= s_conf[li];
+	o_op = dop;
 
 	// ---- cov3D -> scale / rotation (computeCov3D backward) ----
 	if (cov3D_precomp != nullptr) {
-		if (dL_dcov3D) for (int i = 0; i < 6; i++) dL_dcov3D[6 * (size_t)idx + i] = dcov[i];
-		store3(dL_dscales, idx, 0.f, 0.f, 0.f);
-		if (dL_drots) reinterpret_cast<float4*>(dL_drots)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+		for (int i = 0; i < 6; i++) o_cov[i] = dcov[i];
 	} else {
-		if (dL_dcov3D) for (int i = 0; i < 6; i++) dL_dcov3D[6 * (size_t)idx + i] = 0.f;
 		const float r = q.x, x = q.y, y = q.z, z = q.w;
 		// GLM column-major R[col][row]
 		const float R[3][3] = {{1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
@@ -514,7 +601,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
 		float dsc[3];
 #pragma unroll
 		for (int k = 0; k < 3; k++) dsc[k] = R[0][k] * dMt[k][0] + R[1][k] * dMt[k][1] + R[2][k] * dMt[k][2];
-		store3(dL_dscales, idx, dsc[0], dsc[1], dsc[2]);
+		o_sc[0] = dsc[0]; o_sc[1] = dsc[1]; o_sc[2] = dsc[2];
 #pragma unroll
 		for (int k = 0; k < 3; k++)
 #pragma unroll
@@ -524,8 +611,66 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
 		dq.y = 2 * y * (dMt[1][0] + dMt[0][1]) + 2 * z * (dMt[2][0] + dMt[0][2]) + 2 * r * (dMt[1][2] - dMt[2][1]) - 4 * x * (dMt[2][2] + dMt[1][1]);
 		dq.z = 2 * x * (dMt[1][0] + dMt[0][1]) + 2 * r * (dMt[2][0] - dMt[0][2]) + 2 * z * (dMt[1][2] + dMt[2][1]) - 4 * y * (dMt[2][2] + dMt[0][0]);
 		dq.w = 2 * r * (dMt[0][1] - dMt[1][0]) + 2 * x * (dMt[2][0] + dMt[0][2]) + 2 * y * (dMt[1][2] + dMt[2][1]) - 4 * z * (dMt[1][1] + dMt[0][0]);
-		if (dL_drots) reinterpret_cast<float4*>(dL_drots)[idx] = dq;
+		o_rot = dq;
 	}
+	}  // rendered Gaussian
+
+	// ---- write out: rows into the staging buffers, then one bulk store per array (or coalesced copies) ----
+	const bool valid = idx < P;
+	__syncwarp();
+	s_means[3 * li] = o_mean[0]; s_means[3 * li + 1] = o_mean[1]; s_means[3 * li + 2] = o_mean[2];
+	s_o2[3 * li] = o_m2[0]; s_o2[3 * li + 1] = o_m2[1]; s_o2[3 * li + 2] = 0.f;
+	s_oc[3 * li] = o_col[0]; s_oc[3 * li + 1] = o_col[1]; s_oc[3 * li + 2] = o_col[2];
+	const bool feat_out = dL_dfeat != nullptr;  // at most one of dL_dfeat / dL_dshs_lang is requested per call
+	s_feat[3 * li] = feat_out ? o_feat[0] : o_shl[0]; s_feat[3 * li + 1] = feat_out ? o_feat[1] : o_shl[1];
+	s_feat[3 * li + 2] = feat_out ? o_feat[2] : o_shl[2];
+	__syncthreads();  // all reads of s_geo (quaternions live past the scales) are done before it is overwritten
+	if (cov3D_precomp != nullptr) {
+#pragma unroll
+		for (int i = 0; i < 6; i++) s_geo[6 * li + i] = o_cov[i];
+	} else {
+		s_geo[3 * li] = o_sc[0]; s_geo[3 * li + 1] = o_sc[1]; s_geo[3 * li + 2] = o_sc[2];
+	}
+	if (dL_dshs != nullptr) {
+		if (sh_staged) {
+			float* row = s_sh + li * M * 3;
+#pragma unroll
+			for (int k = 0; k < 16; k++) {
+				if (k < M) { row[3 * k] = shw[k] * dRGB[0]; row[3 * k + 1] = shw[k] * dRGB[1]; row[3 * k + 2] = shw[k] * dRGB[2]; }
+			}
+		} else if (valid) {
+			float* row = dL_dshs + (size_t)idx * M * 3;
+#pragma unroll
+			for (int k = 0; k < 16; k++) {
+				if (k < M) { row[3 * k] = shw[k] * dRGB[0]; row[3 * k + 1] = shw[k] * dRGB[1]; row[3 * k + 2] = shw[k] * dRGB[2]; }
+			}
+			for (int i = 48; i < 3 * M; i++) row[i] = 0.f;
+		}
+	}
+	if (valid) {
+		if (dL_dopac) dL_dopac[idx] = o_op;
+		if (dL_drots) reinterpret_cast<float4*>(dL_drots)[idx] = o_rot;
+	}
+	tma_store_fence();
+	__syncthreads();
+	auto put = [&](float* dst, const float* src, int floats_per_item) {
+		if (dst == nullptr) return;
+		float* g = dst + base * floats_per_item;
+		if (full) {
+			if (li == 0) tma_store_1d(g, src, (uint32_t)(PRE_THREADS * floats_per_item * 4));
+		} else {
+			for (int i = li; i < cnt * floats_per_item; i += PRE_THREADS) g[i] = src[i];
+		}
+	};
+	put(dL_dmeans3D, s_means, 3);
+	put(dL_dmeans2D, s_o2, 3);
+	put(dL_dcolors, s_oc, 3);
+	put(dL_dfeat, s_feat, 3);
+	put(dL_dshs_lang, s_feat, 3);
+	if (cov3D_precomp != nullptr) put(dL_dcov3D, s_geo, 6);
+	else put(dL_dscales, s_geo, 3);
+	if (sh_staged) put(dL_dshs, s_sh, 3 * M);
+	if (full && li == 0) { tma_store_commit(); tma_store_wait_read(); }
 }
 
 }  // namespace
@@ -535,12 +680,16 @@ void launch_preprocess_forward(const b200gs_view_t& v, const b200gs_gaussians_t&
 	const int P = g.P;
 	const float focal_y = v.height / (2.0f * v.tan_fovy);  // rasterizer_impl.cu:222-223
 	const float focal_x = v.width / (2.0f * v.tan_fovx);
-	preprocess_forward_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
+	const auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+	const int tma_ok = al16(g.means3D) && al16(g.scales) && al16(g.rotations) && al16(g.opacities) && al16(g.shs) &&
+	                   al16(g.cov3D_precomp) && al16(g.colors_precomp) && al16(g.language_feature_precomp) &&
+	                   al16(g.shs_language) && al16(g.confidence);
+	preprocess_forward_kernel<<<(P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, stream>>>(
 		P, v.sh_degree, v.sh_coeffs, g.means3D, g.scales, v.scale_modifier, g.rotations, g.opacities, g.shs,
 		g.cov3D_precomp, g.colors_precomp, g.language_feature_precomp, g.shs_language, g.confidence,
 		v.viewmatrix, v.projmatrix, v.campos, v.width, v.height, v.tan_fovx, v.tan_fovy, focal_x, focal_y,
 		v.extended, v.prefiltered, radii, gs.depths, gs.rect, gs.rec, gs.clamped, gs.key_a, gs.order, gs.hist, is.ranges,
-		((v.width + TILE_X - 1) / TILE_X) * ((v.height + TILE_Y - 1) / TILE_Y), gs.hdr);
+		((v.width + TILE_X - 1) / TILE_X) * ((v.height + TILE_Y - 1) / TILE_Y), gs.hdr, tma_ok);
 	count_launch();
 }
 
@@ -549,12 +698,17 @@ void launch_preprocess_backward(const b200gs_view_t& v, const b200gs_gaussians_t
 	const int P = g.P;
 	const float focal_y = v.height / (2.0f * v.tan_fovy);
 	const float focal_x = v.width / (2.0f * v.tan_fovx);
-	preprocess_backward_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
+	const auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+	const int tma_ok = al16(g.means3D) && al16(g.scales) && al16(g.rotations) && al16(g.shs) && al16(g.cov3D_precomp) &&
+	                   al16(g.shs_language) && al16(g.confidence) && al16(grec) && al16(gr.dL_dmeans3D) && al16(gr.dL_dmeans2D) &&
+	                   al16(gr.dL_dshs) && al16(gr.dL_dcolors) && al16(gr.dL_dscales) && al16(gr.dL_dcov3D) && al16(gr.dL_dfeatures) &&
+	                   al16(gr.dL_dshs_language);
+	preprocess_backward_kernel<<<(P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, stream>>>(
 		P, v.sh_degree, v.sh_coeffs, g.means3D, radii, g.shs, gs.clamped, g.scales, g.rotations, v.scale_modifier,
 		g.cov3D_precomp, g.language_feature_precomp, g.shs_language, g.confidence, v.viewmatrix, v.projmatrix,
 		v.campos, focal_x, focal_y, v.tan_fovx, v.tan_fovy, v.extended, reinterpret_cast<const float4*>(grec),
 		gr.dL_dmeans3D, gr.dL_dmeans2D, gr.dL_dshs, gr.dL_dcolors, gr.dL_dopacities, gr.dL_dscales,
-		gr.dL_drotations, gr.dL_dcov3D, gr.dL_dfeatures, gr.dL_dshs_language);
+		gr.dL_drotations, gr.dL_dcov3D, gr.dL_dfeatures, gr.dL_dshs_language, tma_ok);
 	count_launch();
 }
 
