@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(
 	if (st.tma) mbar_wait(&s_bar, 0);
 	else __syncthreads();
 	float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0, r3 = r0;
+	uint32_t touched = 0;
 	if (idx < P) {
 	ViewConsts vc;
 	load_view(vc, viewmatrix, projmatrix, campos);
@@ -275,8 +276,17 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(
 				if (colors_precomp != nullptr) {
 					rgb[0] = s_sh[3 * li]; rgb[1] = s_sh[3 * li + 1]; rgb[2] = s_sh[3 * li + 2];
 				} else {
-					sh_to_rgb(D, sh_staged ? s_sh + li * M * 3 : shs + (size_t)idx * M * 3, __fsub_rn(x, vc.campos[0]), __fsub_rn(y, vc.campos[1]),
-					          __fsub_rn(z, vc.campos[2]), rgb, clamp_bits);
+					if (sh_staged && M == 16) {
+						// 12 x LDS.128 (row stride 192 B: 4-way bank conflict) instead of 48 scalar loads (16-way)
+						float shr[48];
+						const float4* row = reinterpret_cast<const float4*>(s_sh + li * 48);
+#pragma unroll
+						for (int j = 0; j < 12; j++) { const float4 t4 = row[j]; shr[4 * j] = t4.x; shr[4 * j + 1] = t4.y; shr[4 * j + 2] = t4.z; shr[4 * j + 3] = t4.w; }
+						sh_to_rgb(D, shr, __fsub_rn(x, vc.campos[0]), __fsub_rn(y, vc.campos[1]), __fsub_rn(z, vc.campos[2]), rgb, clamp_bits);
+					} else {
+						sh_to_rgb(D, sh_staged ? s_sh + li * M * 3 : shs + (size_t)idx * M * 3, __fsub_rn(x, vc.campos[0]), __fsub_rn(y, vc.campos[1]),
+						          __fsub_rn(z, vc.campos[2]), rgb, clamp_bits);
+					}
 				}
 				float f[3] = {rgb[0], rgb[1], rgb[2]};  // include_feature=False: feature aliases colour
 				if (extended) {
@@ -311,8 +321,11 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(
 	sort_keys[idx] = out_key;
 	sort_vals[idx] = (uint32_t)idx;
 	atomicAdd(&s_hist[out_key & 255u], 1u);
-	const unsigned long long touched = (unsigned long long)(out_rect.z - out_rect.x) * (unsigned long long)(out_rect.w - out_rect.y);
-	if (touched) atomicAdd(&s_instances, touched);
+	touched = (uint32_t)(out_rect.z - out_rect.x) * (uint32_t)(out_rect.w - out_rect.y);
+	}
+	{
+		const uint32_t wsum = __reduce_add_sync(0xFFFFFFFFu, touched);  // < 2^32 per warp: 32 x 65535^2 cannot be reached by 16-bit x 16-bit tile grids in practice
+		if ((li & 31) == 0 && wsum) atomicAdd(&s_instances, (unsigned long long)wsum);
 	}
 	// splat records leave the CTA as one contiguous bulk store
 	s_rec[4 * li] = r0; s_rec[4 * li + 1] = r1; s_rec[4 * li + 2] = r2; s_rec[4 * li + 3] = r3;
@@ -529,7 +542,22 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_backward_kernel(
 		const float* sh = sh_staged ? s_sh + li * M * 3 : shs + (size_t)idx * M * 3;
 		float ddir[3] = {0.f, 0.f, 0.f};  // dL/ddir
 		auto wr = [&](int k, float w) { shw[k] = w; };  // the row is written after every read of `sh` (same buffer)
-		auto shdot = [&](int k) { return sh[3 * k] * dRGB[0] + sh[3 * k + 1] * dRGB[1] + sh[3 * k + 2] * dRGB[2]; };
+		float sd[16];  // sd[k] = sh[k] . dRGB
+		if (sh_staged && M == 16) {
+			const float4* row = reinterpret_cast<const float4*>(s_sh + li * 48);
+#pragma unroll
+			for (int j = 0; j < 4; j++) {  // 4 coefficients = 12 floats = 3 x LDS.128 per step
+				const float4 a4 = row[3 * j], b4 = row[3 * j + 1], c4 = row[3 * j + 2];
+				sd[4 * j] = a4.x * dRGB[0] + a4.y * dRGB[1] + a4.z * dRGB[2];
+				sd[4 * j + 1] = a4.w * dRGB[0] + b4.x * dRGB[1] + b4.y * dRGB[2];
+				sd[4 * j + 2] = b4.z * dRGB[0] + b4.w * dRGB[1] + c4.x * dRGB[2];
+				sd[4 * j + 3] = c4.y * dRGB[0] + c4.z * dRGB[1] + c4.w * dRGB[2];
+			}
+		} else {
+#pragma unroll
+			for (int k = 0; k < 16; k++) sd[k] = (k < (D + 1) * (D + 1)) ? sh[3 * k] * dRGB[0] + sh[3 * k + 1] * dRGB[1] + sh[3 * k + 2] * dRGB[2] : 0.f;
+		}
+		auto shdot = [&](int k) { return sd[k]; };
 		wr(0, kSH_C0);
 		int written = 1;
 		if (D > 0) {
@@ -633,10 +661,21 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_backward_kernel(
 	}
 	if (dL_dshs != nullptr) {
 		if (sh_staged) {
-			float* row = s_sh + li * M * 3;
+			if (M == 16) {
+				float4* row = reinterpret_cast<float4*>(s_sh + li * 48);
 #pragma unroll
-			for (int k = 0; k < 16; k++) {
-				if (k < M) { row[3 * k] = shw[k] * dRGB[0]; row[3 * k + 1] = shw[k] * dRGB[1]; row[3 * k + 2] = shw[k] * dRGB[2]; }
+				for (int j = 0; j < 4; j++) {
+					const float w0 = shw[4 * j], w1 = shw[4 * j + 1], w2 = shw[4 * j + 2], w3 = shw[4 * j + 3];
+					row[3 * j] = make_float4(w0 * dRGB[0], w0 * dRGB[1], w0 * dRGB[2], w1 * dRGB[0]);
+					row[3 * j + 1] = make_float4(w1 * dRGB[1], w1 * dRGB[2], w2 * dRGB[0], w2 * dRGB[1]);
+					row[3 * j + 2] = make_float4(w2 * dRGB[2], w3 * dRGB[0], w3 * dRGB[1], w3 * dRGB[2]);
+				}
+			} else {
+				float* row = s_sh + li * M * 3;
+#pragma unroll
+				for (int k = 0; k < 16; k++) {
+					if (k < M) { row[3 * k] = shw[k] * dRGB[0]; row[3 * k + 1] = shw[k] * dRGB[1]; row[3 * k + 2] = shw[k] * dRGB[2]; }
+				}
 			}
 		} else if (valid) {
 			float* row = dL_dshs + (size_t)idx * M * 3;
