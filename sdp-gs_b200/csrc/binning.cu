@@ -25,7 +25,8 @@ constexpr uint32_t FLAG_LOCAL = 1u << 30;   // word holds this tile's own count
 constexpr uint32_t FLAG_INCL = 2u << 30;    // word holds the inclusive count over tiles [0..t]
 constexpr uint32_t FLAG_MASK = 3u << 30;
 constexpr uint32_t VALUE_MASK = ~FLAG_MASK;
-constexpr int LOOKBACK_WINDOW = 8;          // predecessors inspected per step (independent loads in flight)
+constexpr int LOOKBACK_WINDOW = 32;         // predecessors inspected per step (independent loads in flight): the INCLUSIVE
+                                            // frontier advances this many tiles per L2 round trip
 
 __device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 __device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
@@ -308,10 +309,12 @@ __global__ void __launch_bounds__(256) tile_ranges_schedule_kernel(
 	__shared__ bool s_last;
 	__shared__ uint32_t s_cnt[128];
 	__shared__ uint32_t s_off[128];
-	__threadfence();
 	__syncthreads();
 	const int tid = threadIdx.x;
-	if (tid == 0) s_last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
+	if (tid == 0) {
+		__threadfence();  // cumulative: orders the whole CTA's range writes (observed through the barrier) before the ticket
+		s_last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
+	}
 	if (tid < 128) s_cnt[tid] = 0;
 	__syncthreads();
 	if (!s_last) return;
