@@ -25,7 +25,7 @@ constexpr uint32_t FLAG_LOCAL = 1u << 30;   // word holds this tile's own count
 constexpr uint32_t FLAG_INCL = 2u << 30;    // word holds the inclusive count over tiles [0..t]
 constexpr uint32_t FLAG_MASK = 3u << 30;
 constexpr uint32_t VALUE_MASK = ~FLAG_MASK;
-constexpr int LOOKBACK_WINDOW = 32;         // predecessors inspected per step (independent loads in flight): the INCLUSIVE
+constexpr int LOOKBACK_WINDOW = 8;          // predecessors inspected per step (independent loads in flight): the INCLUSIVE
                                             // frontier advances this many tiles per L2 round trip
 
 __device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
