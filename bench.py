@@ -509,13 +509,14 @@ def run_reference(args, rank, world, local):
     calls = 3 if ext else 1
     print(json.dumps(dict(
         impl="reference", metric="rasterizer fwd+bwd views/s (1000/ms_per_step = ms/view; one view per train iteration)",
-        value=1000.0 / ms_per_step, unit="views/s", n_gpus=1, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step,
+        value=1000.0 / ms_per_step, unit="views/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step,
         higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
         config=dict(workload=f"{args.workload}: P={P} Gaussians, {wl.W}x{wl.H}, SH degree 3 in-kernel, "
                              f"outputs={'color+depth+alpha+feature via 3 channel-packed calls' if ext else 'color'}",
                     P=P, width=wl.W, height=wl.H, mode=args.mode, reference_calls_per_step=calls,
                     l2="flushed between steps (256 MiB write)",
-                    note="unmodified reference CUDA rasterizer (diff-gaussian-rasterization) built for sm_100a, torch-free shim"),
+                    note="unmodified reference CUDA rasterizer (diff-gaussian-rasterization) built for sm_100a, torch-free shim; "
+                         "the reference has no distributed path: it runs on rank 0's GPU only, whatever N is"),
         e2e=dict(value=args.steps / e2e_sec, unit="views/s", ms_per_step=1000.0 * e2e_sec / args.steps,
                  h2d_bytes_per_step=wl.h2d_bytes, d2h_bytes_per_step=4 + 4 * calls),
         gpu_launches=0, clocks=clocks, vanilla=vanilla,
@@ -525,6 +526,10 @@ def run_reference(args, rank, world, local):
 
 
 def main():
+    # NCCL and friends write banners to fd 1; the contract is ONE JSON line on stdout, so everything else goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     args = parse()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
@@ -533,6 +538,7 @@ def main():
         run_reference(args, rank, world, local)
     else:
         run_b200gs(args, rank, world, local)
+    sys.stdout.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

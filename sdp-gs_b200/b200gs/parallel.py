@@ -79,18 +79,40 @@ class FusedGradBuffer:
             self.seg["language_feature"].add_(d_feature)
         self.add_statistics(viewspace_grad, radii)
 
-    def all_reduce(self, async_op=False):
-        """SUM over ranks of the fused buffer, MAX of max_radii2D."""
+    @property
+    def grads_flat(self):
+        """The 62 parameter-gradient floats per Gaussian (everything before the two statistics segments)."""
+        return self.flat[: 62 * self.P]
+
+    @property
+    def stats_flat(self):
+        return self.flat[62 * self.P:]
+
+    def all_reduce(self, async_op=False, with_statistics=False):
+        """SUM over ranks of the parameter gradients: ONE collective per training step.  The densification
+        statistics are sums / maxima over iterations as well as over ranks, so they only need combining when
+        densify_and_prune is about to read them (every `densification_interval` steps, train.py:223-225):
+        pass with_statistics=True then, or call all_reduce_statistics()."""
         rank, n = world()
         if n == 1:
             return None
-        w1 = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=True)
-        w2 = dist.all_reduce(self.max_radii2D, op=dist.ReduceOp.MAX, async_op=True)
+        works = [dist.all_reduce(self.flat if with_statistics else self.grads_flat, op=dist.ReduceOp.SUM, async_op=True)]
+        if with_statistics:
+            works.append(dist.all_reduce(self.max_radii2D, op=dist.ReduceOp.MAX, async_op=True))
         if async_op:
-            return (w1, w2)
+            return works
+        for w in works:
+            w.wait()
+        return None
+
+    def all_reduce_statistics(self):
+        rank, n = world()
+        if n == 1:
+            return
+        w1 = dist.all_reduce(self.stats_flat, op=dist.ReduceOp.SUM, async_op=True)
+        w2 = dist.all_reduce(self.max_radii2D, op=dist.ReduceOp.MAX, async_op=True)
         w1.wait()
         w2.wait()
-        return None
 
 
 def render_views_sharded(render_fn, n_views, gather=False):
@@ -117,5 +139,5 @@ def image_parallel_step(fwd_bwd_fn, view_indices, bucket):
     bucket.zero_()
     for k in shard_views(len(view_indices), rank, n):
         bucket.accumulate_view(**fwd_bwd_fn(view_indices[k]))
-    bucket.all_reduce()
+    bucket.all_reduce(with_statistics=True)
     return bucket
