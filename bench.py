@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--mode", default="extended", choices=["extended", "vanilla"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--P", type=int, default=None, help="override the Gaussian count of the workload")
+    ap.add_argument("--fwd-only", action="store_true", help="forward only (render throughput, BASELINE configs[3])")
     return ap.parse_args()
 
 
@@ -237,16 +238,17 @@ def run_b200gs(args, rank, world, local):
         s = rz.RasterSession(wl.settings(cam, P), means3D=wl.devt["means3D"], opacities=wl.devt["opacities"], shs=wl.devt["shs"],
                              scales=wl.devt["scales"], rotations=wl.devt["rotations"],
                              language_feature_precomp=wl.devt.get("features"), extended=ext, capacity=capacity,
-                             grads_out=grads_out)
-        s.cot["color"].copy_(wl.cot[vi][0])
-        if ext:
-            s.cot["depth"].copy_(wl.cot[vi][1]); s.cot["alpha"].copy_(wl.cot[vi][2]); s.cot["feature"].copy_(wl.cot[vi][3])
+                             grads_out=grads_out, with_backward=not args.fwd_only)
+        if not args.fwd_only:
+            s.cot["color"].copy_(wl.cot[vi][0])
+            if ext:
+                s.cot["depth"].copy_(wl.cot[vi][1]); s.cot["alpha"].copy_(wl.cot[vi][2]); s.cot["feature"].copy_(wl.cot[vi][3])
         s.capture()
         sessions.append(s)
 
     def step_resident(i):
         sessions[(i + rank) % nviews].replay()
-        if world > 1:
+        if world > 1 and not args.fwd_only:
             bucket.all_reduce()
 
     sampler = ClockSampler(local)
@@ -297,6 +299,10 @@ def run_b200gs(args, rank, world, local):
                   rotations=t["rotations"])
         if ext:
             kw["language_feature_precomp"] = t["features"]
+        if args.fwd_only:
+            with torch.no_grad():
+                outs = GaussianRasterizer(rs)(**kw)
+            return float(outs[0].sum().item())
         outs = GaussianRasterizer(rs)(**kw)
         cot = wl.cot[vi]
         if ext:
@@ -315,7 +321,7 @@ def run_b200gs(args, rank, world, local):
 
     # ---- vanilla single-call comparison point (colour only), device resident
     vanilla = None
-    if ext and world == 1:
+    if ext and world == 1 and not args.fwd_only:
         wv = Workload(args.workload, "vanilla", dev, args.P)
         sv = []
         for vi, cam in enumerate(wv.cams):
@@ -328,7 +334,10 @@ def run_b200gs(args, rank, world, local):
 
     # ---- roofline of the dominant kernel + whole step
     L, V = int(np.mean(Ls)), int(np.mean(Vs))
-    model = stage_bytes(P, V, L, wl.W, wl.H, sh_degree=3, sh_coeffs=16, use_sh=True, extended=ext, training=True)
+    model = stage_bytes(P, V, L, wl.W, wl.H, sh_degree=3, sh_coeffs=16, use_sh=True, extended=ext, training=not args.fwd_only)
+    if args.fwd_only:
+        model["backward"] = {k: 0 for k in model["backward"]}
+        model["bytes_bwd"] = 0
     peak, peak_src = peaks()
     by_stage = {"preprocess": model["forward"]["preprocess"], "depth_sort": 0, "scan": model["forward"]["scan"],
                 "duplicate": model["forward"]["duplicate"], "tile_sort": model["forward"]["sort"],
@@ -363,7 +372,7 @@ def run_b200gs(args, rank, world, local):
                     value=value, unit="views/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step,
                     higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                     config=dict(workload=f"{args.workload}: P={P} Gaussians, {wl.W}x{wl.H}, SH degree 3 in-kernel, "
-                                         f"outputs={'color+depth+alpha+feature' if ext else 'color'}, one view fwd+bwd per step"
+                                         f"outputs={'color+depth+alpha+feature' if ext else 'color'}, one view {'forward' if args.fwd_only else 'fwd+bwd'} per step"
                                          + (", per-Gaussian gradient NCCL all-reduce (image-parallel)" if world > 1 else ""),
                                 P=P, width=wl.W, height=wl.H, mode=args.mode, num_rendered=L, visible=V, tiles=model["tiles"],
                                 sort_passes_model=model["passes"], l2="flushed between steps (256 MiB write)",
@@ -423,6 +432,8 @@ class RefBench:
             t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
             self.cams.append((cam, t(cam.viewmatrix), t(cam.projmatrix), t(cam.campos)))
 
+    fwd_only = False
+
     def fwd_bwd(self, vi, T, shs, colors, bg, dpix, D):
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
         cam, view, proj, campos = self.cams[vi]
@@ -435,6 +446,8 @@ class RefBench:
                                p(self.img), C.c_size_t(self.ib), C.c_int(0))
         if n < 0:
             raise RuntimeError("reference forward failed: " + self.L.ref_last_error().decode())
+        if self.fwd_only:
+            return n
         for t in self.g.values():  # the nine torch::zeros of rasterize_points.cu:151-159
             t.zero_()
         g = self.g
@@ -477,6 +490,7 @@ def run_reference(args, rank, world, local):
     s0 = ref_cuda.forward(wl.host["means3D"], wl.host["opacities"], wl.cams[0], np.zeros(3, np.float32), shs=wl.host["shs"],
                           scales=wl.host["scales"], rotations=wl.host["rotations"], decode=False)
     rb = RefBench(wl, int(s0.binning.numel() * 1.3))
+    rb.fwd_only = args.fwd_only
     del s0
     H, W = wl.H, wl.W
     if ext:
