@@ -69,6 +69,40 @@ __device__ __forceinline__ uint32_t lookback_exclusive(uint32_t* __restrict__ co
 	return excl;
 }
 
+// Same contract, executed by one full warp on a stride-1 column: the 32 lanes inspect 32 consecutive predecessors
+// with one coalesced request, so the INCLUSIVE frontier moves 32 tiles per L2 round trip.  Result valid in all lanes.
+__device__ __forceinline__ uint32_t lookback_exclusive_warp(uint32_t* __restrict__ column, uint32_t tile, uint32_t mine) {
+	const unsigned lane = threadIdx.x & 31;
+	if (tile == 0) {
+		if (lane == 0) st_volatile(column, mine | FLAG_INCL);
+		return 0;
+	}
+	if (lane == 0) st_volatile(column + tile, mine | FLAG_LOCAL);
+	uint32_t excl = 0;
+	int64_t t = (int64_t)tile - 1;
+	while (true) {
+		const int64_t mine_t = t - lane;
+		uint32_t w = mine_t >= 0 ? ld_volatile(column + mine_t) : FLAG_INCL;
+		unsigned first, need;
+		while (true) {
+			const unsigned incl = __ballot_sync(0xFFFFFFFFu, (w & FLAG_INCL) != 0);
+			const unsigned ready = __ballot_sync(0xFFFFFFFFu, (w & FLAG_MASK) != 0);
+			first = incl ? (unsigned)(__ffs(incl) - 1) : 32u;
+			need = first >= 31u ? 0xFFFFFFFFu : ((2u << first) - 1u);
+			if ((ready & need) == need) break;
+			if ((w & FLAG_MASK) == 0) w = ld_volatile(column + mine_t);
+		}
+		uint32_t v = ((need >> lane) & 1u) ? (w & VALUE_MASK) : 0u;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+		excl += v;
+		if (first < 32u) break;
+		t -= 32;
+	}
+	if (lane == 0) st_volatile(column + tile, (excl + mine) | FLAG_INCL);
+	return excl;
+}
+
 template <int ITEMS>
 __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(
 	const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
@@ -111,7 +145,17 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(
 		const bool valid = li < tile_n;
 		key[j] = valid ? keys_in[tile_base + li] : 0xFFFFFFFFu;
 		val[j] = valid ? vals_in[tile_base + li] : 0u;
-		if (valid && next_hist != nullptr) atomicAdd(&s_next[(key[j] >> next_shift) & nmask], 1u);
+		if (next_hist != nullptr) {
+			const uint32_t nd = (key[j] >> next_shift) & nmask;
+			if (next_bits <= 3) {  // few bins: every thread would hit the same shared words, count with ballots instead
+				for (uint32_t b = 0; b <= nmask; b++) {
+					const unsigned m = __ballot_sync(0xFFFFFFFFu, valid && nd == b);
+					if (lane == 0 && m) atomicAdd(&s_next[b], (uint32_t)__popc(m));
+				}
+			} else if (valid) {
+				atomicAdd(&s_next[nd], 1u);
+			}
+		}
 	}
 	__syncthreads();
 	if (next_hist != nullptr && s_next[tid]) atomicAdd(next_hist + tid, s_next[tid]);
@@ -210,7 +254,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(
 	__shared__ uint32_t s_tile;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	if (tid == 0) s_tile = atomicAdd(&hdr->scan_ticket, 1u);
-	s_hist[tid] = 0;
+	if (tid < 256) s_hist[tid] = 0;
 	// zero the tile sort's look-back words (they are first read by the next kernel)
 	for (size_t i = (size_t)blockIdx.x * EMIT_THREADS + tid; i < zero_count; i += (size_t)gridDim.x * EMIT_THREADS) zero_words[i] = 0;
 	__syncthreads();
@@ -243,10 +287,10 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(
 		if (w < warp) wpre += s_warp[w];
 		total += s_warp[w];
 	}
-	if (tid == 0) {
-		const uint32_t excl = lookback_exclusive(scan_state, 1, tile, total);
-		s_prefix = excl;
-		if ((int64_t)(tile + 1) * TILE >= P) {  // last tile: instance count, overflow flag
+	if (warp == 0) {
+		const uint32_t excl = lookback_exclusive_warp(scan_state, tile, total);
+		if (lane == 0) s_prefix = excl;
+		if (lane == 0 && (int64_t)(tile + 1) * TILE >= P) {  // last tile: instance count, overflow flag
 			const unsigned long long L = (unsigned long long)excl + total;  // == hdr->num_rendered (summed by preprocess)
 			if (L > (unsigned long long)capacity) atomicOr(&hdr->overflow, 1u);
 		}
@@ -285,7 +329,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(
 		start += n[k];
 	}
 	__syncthreads();
-	if (s_hist[tid]) atomicAdd(tile_hist + tid, s_hist[tid]);
+	if (tid < 256 && s_hist[tid]) atomicAdd(tile_hist + tid, s_hist[tid]);
 }
 
 // K5: identifyTileRanges (rasterizer_impl.cu:116-138; `ranges` zero-initialised by the preprocess kernel, :310),

@@ -73,7 +73,7 @@ static inline int64_t sort_tiles_for(int64_t n) {
 	int64_t per = (int64_t)SORT_THREADS * sort_items_for(n);
 	return (n + per - 1) / per;
 }
-#define SCAN_THREADS 256
+#define SCAN_THREADS 1024
 #define SCAN_ITEMS 1  // Gaussians per thread in scan_emit_kernel (binning.cu: EMIT_THREADS x EMIT_ITEMS must match)
 static inline int64_t scan_tiles_for(int64_t n) { return (n + SCAN_THREADS * SCAN_ITEMS - 1) / (SCAN_THREADS * SCAN_ITEMS); }
 
