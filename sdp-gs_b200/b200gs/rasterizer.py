@@ -20,12 +20,46 @@ from ._lib import Gaussians, GradOutputs, Grads, Outputs, View, Workspace, check
 _CAPACITY = None
 
 
+_AUTO = {}      # (P, W, H, device) -> capacity learned from earlier forwards ("auto" mode)
+_PENDING = []   # [(event, pinned header copy, key)] status read-backs of earlier no-sync forwards, checked lazily
+
+
 def set_binning_capacity(capacity):
-    """None (default): size the binning workspace exactly, with one 8-byte D2H sync per forward, as the
-    reference does.  int: no host sync; the forward drops instances beyond `capacity` and
-    `last_forward_status()` reports the overflow."""
+    """How the binning workspace (one slot per (Gaussian, tile) instance) is sized.
+    None (default): exactly, with one 8-byte D2H sync per forward, as the reference does (rasterizer_impl.cu:281).
+    int: no host sync; instances beyond `capacity` are dropped and the overflow flag is raised on the device.
+    "auto": the first forward of a given (P, W, H) runs in exact mode; later ones run without any host sync with
+      1.3x the largest instance count seen so far.  Each forward's status word is copied back asynchronously and
+      checked at the next call: an overflow (the scene changed so much that the margin was exceeded) raises a
+      B200GSError one call late and the capacity is re-learned."""
     global _CAPACITY
-    _CAPACITY = None if capacity is None else int(capacity)
+    _CAPACITY = capacity if (capacity is None or capacity == "auto") else int(capacity)
+    if capacity != "auto":
+        _AUTO.clear()
+        _PENDING.clear()
+
+
+def _check_pending(block=False):
+    """Inspect completed status read-backs of earlier "auto" forwards."""
+    import numpy as np
+    keep = []
+    err = None
+    for ev, host, key in _PENDING:
+        if not block and not ev.query():
+            keep.append((ev, host, key))
+            continue
+        if block:
+            ev.synchronize()
+        words = host.numpy().view(np.uint64)
+        n = int(words[0])
+        overflow = int(host.numpy().view(np.uint32)[2])
+        if n * 1.15 > _AUTO.get(key, 0):
+            _AUTO[key] = int(n * 1.3) + 4096
+        if overflow & 1:
+            err = _lib.B200GSError(f"binning capacity overflow in an earlier forward (num_rendered={n}); capacity re-learned")
+    _PENDING[:] = keep
+    if err is not None:
+        raise err
 
 
 def _ptr(t):
@@ -119,16 +153,29 @@ def _forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations,
             depth.zero_(); alpha.zero_(); feature.zero_()
         binning = torch.empty((0,), dtype=torch.uint8, device=dev)
         return 0, 0, color, depth, alpha, feature, radii, geom, binning, img
-    if _CAPACITY is None:
+    auto_key = None
+    if _CAPACITY == "auto":
+        _check_pending()
+        auto_key = (P, W, H, str(dev))
+    if _CAPACITY is None or (auto_key is not None and auto_key not in _AUTO):
         n = C.c_int64(0)
         check(lib.b200gs_forward_preprocess(C.byref(v), C.byref(g), C.byref(o), C.byref(ws), stream, C.byref(n)))
         num_rendered, capacity = int(n.value), int(n.value)
+        if auto_key is not None:
+            _AUTO[auto_key] = int(n.value * 1.3) + 4096
+            auto_key = None  # exact this time, nothing to verify
     else:
         check(lib.b200gs_forward_preprocess(C.byref(v), C.byref(g), C.byref(o), C.byref(ws), stream, None))
-        num_rendered, capacity = -1, int(_CAPACITY)
+        num_rendered, capacity = -1, int(_AUTO[auto_key] if auto_key is not None else _CAPACITY)
     binning = torch.empty((lib.b200gs_binning_bytes(capacity),), dtype=torch.uint8, device=dev)
     ws.binning, ws.binning_bytes = binning.data_ptr(), binning.numel()
     check(lib.b200gs_forward_render(C.byref(v), C.byref(g), C.byref(o), C.byref(ws), C.c_int64(capacity), stream))
+    if auto_key is not None:  # asynchronous read-back of {num_rendered, overflow}; looked at by a later call
+        host = torch.empty((16,), dtype=torch.uint8, pin_memory=True)
+        host.copy_(geom[:16], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        _PENDING.append((ev, host, auto_key))
     del keep
     return num_rendered, capacity, color, depth, alpha, feature, radii, geom, binning, img
 

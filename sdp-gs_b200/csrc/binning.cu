@@ -145,17 +145,7 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(
 		const bool valid = li < tile_n;
 		key[j] = valid ? keys_in[tile_base + li] : 0xFFFFFFFFu;
 		val[j] = valid ? vals_in[tile_base + li] : 0u;
-		if (next_hist != nullptr) {
-			const uint32_t nd = (key[j] >> next_shift) & nmask;
-			if (next_bits <= 3) {  // few bins: every thread would hit the same shared words, count with ballots instead
-				for (uint32_t b = 0; b <= nmask; b++) {
-					const unsigned m = __ballot_sync(0xFFFFFFFFu, valid && nd == b);
-					if (lane == 0 && m) atomicAdd(&s_next[b], (uint32_t)__popc(m));
-				}
-			} else if (valid) {
-				atomicAdd(&s_next[nd], 1u);
-			}
-		}
+		if (valid && next_hist != nullptr) atomicAdd(&s_next[(key[j] >> next_shift) & nmask], 1u);
 	}
 	__syncthreads();
 	if (next_hist != nullptr && s_next[tid]) atomicAdd(next_hist + tid, s_next[tid]);

@@ -249,3 +249,32 @@ def test_capacity_mode_and_overflow_flag():
     n, ov = C.c_int64(0), C.c_int32(0)
     rc = _lib.lib.b200gs_forward_status(C.byref(ws), None, C.byref(n), C.byref(ov))
     assert rc == -3 and ov.value == 1 and n.value == L
+
+
+def test_auto_capacity_mode():
+    """"auto": exact first call, no-sync afterwards with identical results; an overflow is reported one call late."""
+    _require_cuda()
+    import torch
+    from b200gs import _lib, rasterizer as rz
+    inp = case_inputs("small_sh3")
+    base = run_product(inp, backward=False)
+    try:
+        rz.set_binning_capacity("auto")
+        a = run_product(inp, backward=False)   # learns the capacity (exact mode)
+        b = run_product(inp, True)             # no host sync
+        np.testing.assert_array_equal(bits(a["color"]), bits(base["color"]))
+        np.testing.assert_array_equal(bits(b["color"]), bits(base["color"]))
+        np.testing.assert_array_equal(b["point_list"], base["point_list"])
+        rz._check_pending(block=True)
+        big = dict(inp)
+        big["scale_modifier"] = 3.0            # same (P, W, H), ~9x the footprint: exceeds the learned margin
+        run_product(big, backward=False)
+        with pytest.raises(_lib.B200GSError, match="overflow"):
+            torch.cuda.synchronize()
+            rz._check_pending(block=True)
+        c = run_product(big, backward=False)   # capacity was re-learned from the true count
+        rz._check_pending(block=True)
+    finally:
+        rz.set_binning_capacity(None)
+    exact = run_product(big, backward=False)
+    np.testing.assert_array_equal(bits(c["color"]), bits(exact["color"]))
