@@ -177,7 +177,9 @@ def run_product(inp, backward=True, cot=None, dev="cuda"):
     res["n_contrib"] = view(img, off3[1], np.uint32, W * H).reshape(H, W)
     res["ranges"] = view(img, off3[2], np.uint32, 2 * tiles).reshape(tiles, 2)
     off2 = (C.c_int64 * 2)()
-    _lib.lib.b200gs_binning_layout(W, H, int(getattr(node, "capacity", L)), off2)  # layout depends on the workspace capacity
+    cap = int(getattr(node, "capacity", L))
+    _lib.lib.b200gs_binning_layout(W, H, cap, off2)  # layout depends on the workspace capacity
+    L = min(L, cap)  # instances beyond the capacity were dropped (overflow flag raised)
     res["point_list"] = view(binning, off2[0], np.uint32, L) if L else np.zeros(0, np.uint32)
     tile_ids = view(binning, off2[1], np.uint32, L) if L else np.zeros(0, np.uint32)
     dbits = depths.view(np.uint32)
