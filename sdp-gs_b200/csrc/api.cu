@@ -9,6 +9,7 @@
 #include <vector>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "common.cuh"
 
@@ -72,6 +73,15 @@ int check_stage(const b200gs_view_t* v, cudaStream_t s, const char* what) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+unsigned pdl_mask() {
+	static int v = -1;
+	if (v < 0) {
+		const char* e = getenv("B200GS_PDL");
+		v = e ? (int)(strtoul(e, nullptr, 0) & 0xFFu) : 0xFF;
+	}
+	return (unsigned)v;
+}
+
 uint32_t higher_msb(uint32_t n) {
 	uint32_t msb = sizeof(n) * 4, step = msb;
 	while (step > 1) {
@@ -116,6 +126,7 @@ ImageState image_from_chunk(char* base, int W, int H) {
 	carve(p, s.tile_order, tiles ? tiles : 1);
 	carve(p, s.final_T, N ? N : 1);
 	carve(p, s.n_contrib, N ? N : 1);
+	carve(p, s.tile_count, (tiles ? tiles : 1) * (size_t)tile_count_stride());
 	s.bytes = align_up((size_t)(p - base), 256) + 256;
 	return s;
 }
@@ -257,8 +268,8 @@ int b200gs_forward_preprocess(const b200gs_view_t* v, const b200gs_gaussians_t* 
 	return 0;
 }
 
-int b200gs_forward_render(const b200gs_view_t* v, const b200gs_gaussians_t* g, const b200gs_outputs_t* out,
-                          const b200gs_workspace_t* ws, int64_t capacity, void* stream_) {
+static int forward_render_impl(const b200gs_view_t* v, const b200gs_gaussians_t* g, const b200gs_outputs_t* out,
+                               const b200gs_workspace_t* ws, int64_t capacity, void* stream_, bool chained) {
 	if (int e = validate(v, g, ws)) return e;
 	if (!out || !out->color) return fail(B200GS_E_ARG, "color output is required");
 	if (v->extended && (!out->depth || !out->alpha || !out->feature)) return fail(B200GS_E_ARG, "extended outputs are required");
@@ -271,22 +282,31 @@ int b200gs_forward_render(const b200gs_view_t* v, const b200gs_gaussians_t* g, c
 	ImageState is = image_from_chunk(reinterpret_cast<char*>(ws->image), v->width, v->height);
 	BinningState bs = binning_from_chunk(reinterpret_cast<char*>(ws->binning), v->width, v->height, capacity);
 	resolve_sorted(v, bs);
+	const size_t tiles = (size_t)((v->width + TILE_X - 1) / TILE_X) * ((v->height + TILE_Y - 1) / TILE_Y);
 	if (P > 0 && capacity > 0) {
-		{ StageScope t(stream, ST_EMIT); launch_scan_emit(*v, gs, bs, P, capacity, stream); }
+		{ StageScope t(stream, ST_EMIT); launch_scan_emit(*v, gs, bs, is, P, capacity, stream, chained); }
 		if (int e = check_stage(v, stream, "instance offsets / duplicate-with-keys")) return e;
 		{ StageScope t(stream, ST_TILE_SORT); launch_tile_sort(*v, gs, bs, capacity, stream); }
 		if (int e = check_stage(v, stream, "tile sort")) return e;
 	}
-	{ StageScope t(stream, ST_RANGES); launch_tile_ranges(*v, gs, bs, is, (P > 0) ? capacity : 0, stream); }
-	if (int e = check_stage(v, stream, "tile ranges / schedule")) return e;
+	const bool emitted = P > 0 && capacity > 0;
+	if (!emitted || !tile_counts_path((int)tiles)) {  // small tile grids: scan_emit's last CTA already built ranges + schedule
+		{ StageScope t(stream, ST_RANGES); launch_tile_ranges(*v, gs, bs, is, emitted ? capacity : 0, stream); }
+		if (int e = check_stage(v, stream, "tile ranges / schedule")) return e;
+	}
 	{ StageScope t(stream, ST_BLEND_FWD); launch_blend_forward(*v, gs, bs, is, *out, stream); }
 	return check_stage(v, stream, "blend forward");
+}
+
+int b200gs_forward_render(const b200gs_view_t* v, const b200gs_gaussians_t* g, const b200gs_outputs_t* out,
+                          const b200gs_workspace_t* ws, int64_t capacity, void* stream) {
+	return forward_render_impl(v, g, out, ws, capacity, stream, false);
 }
 
 int b200gs_forward(const b200gs_view_t* v, const b200gs_gaussians_t* g, const b200gs_outputs_t* out,
                    const b200gs_workspace_t* ws, int64_t capacity, void* stream) {
 	if (int e = b200gs_forward_preprocess(v, g, out, ws, stream, nullptr)) return e;
-	return b200gs_forward_render(v, g, out, ws, capacity, stream);
+	return forward_render_impl(v, g, out, ws, capacity, stream, g->P > 0);
 }
 
 int b200gs_forward_status(const b200gs_workspace_t* ws, void* stream_, int64_t* num_rendered, int32_t* overflow) {

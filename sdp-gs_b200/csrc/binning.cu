@@ -33,7 +33,7 @@ __device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) { *reinterp
 
 __device__ __forceinline__ int64_t load_count(const unsigned long long* n_dev, int64_t n_max) {
 	if (n_dev == nullptr) return n_max;
-	unsigned long long n = *n_dev;
+	unsigned long long n = __ldcg(n_dev);
 	return n < (unsigned long long)n_max ? (int64_t)n : n_max;
 }
 
@@ -123,12 +123,14 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(
 	__shared__ int s_trivial;
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int64_t n = load_count(n_dev, n_max);
-	if (tid == 0) { s_tile = atomicAdd(ticket, 1u); s_trivial = 0; }
+	pdl_trigger();
 	for (int i = tid; i < WARPS * 256; i += SORT_THREADS) (&s_warp_hist[0][0])[i] = 0;
 	s_next[tid] = 0;
+	pdl_wait();
+	const int64_t n = load_count(n_dev, n_max);
+	if (tid == 0) { s_tile = atomicAdd(ticket, 1u); s_trivial = 0; }
 	__syncthreads();
-	if ((int64_t)hist[tid] == n && n > 0) s_trivial = 1;  // every key has the same digit: the pass is the identity permutation
+	if ((int64_t)__ldcg(hist + tid) == n && n > 0) s_trivial = 1;  // every key has the same digit: the pass is the identity permutation
 	const uint32_t tile = s_tile;
 	const int64_t tile_base = (int64_t)tile * TILE;
 	if (tile_base >= n) return;
@@ -143,8 +145,8 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(
 	for (int j = 0; j < ITEMS; j++) {
 		const int li = warp_base + j * 32 + lane;
 		const bool valid = li < tile_n;
-		key[j] = valid ? keys_in[tile_base + li] : 0xFFFFFFFFu;
-		val[j] = valid ? vals_in[tile_base + li] : 0u;
+		key[j] = valid ? __ldcg(keys_in + tile_base + li) : 0xFFFFFFFFu;  // .cg, never .nc: see the note on pdl_wait() in common.cuh
+		val[j] = valid ? __ldcg(vals_in + tile_base + li) : 0u;
 		if (valid && next_hist != nullptr) atomicAdd(&s_next[(key[j] >> next_shift) & nmask], 1u);
 	}
 	__syncthreads();
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(
 		}
 		const uint32_t excl = lookback_exclusive(lookback + d, 256, tile, tile_count);
 		// exclusive scan of the global digit histogram and of the tile counts across the 256 digits
-		const uint32_t g = hist[d], l = tile_count;
+		const uint32_t g = __ldcg(hist + d), l = tile_count;
 		uint32_t gi = g, li = l;
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1) {
@@ -231,20 +233,37 @@ constexpr int EMIT_THREADS = SCAN_THREADS;
 constexpr int EMIT_ITEMS = SCAN_ITEMS;
 constexpr uint32_t EMIT_SMALL = 12;
 
+// TILE_COUNTS (images of at most COUNT_TILES_MAX tiles): every emitted instance is also counted into its tile, in
+// shared memory, and each CTA adds its non-zero counters to a global per-tile array (one counter per 128-byte
+// line: L2 atomics on neighbouring words serialise).  The last CTA to finish turns the totals into the tile
+// ranges, the digit histograms of the tile sort and the blend schedule, so no kernel has to re-read the sorted
+// keys.  Larger tile grids keep the separate ranges kernel (a per-instance global RED costs more than it saves).
+constexpr int COUNT_TILES_MAX = 2048;
+constexpr int COUNT_STRIDE = 32;  // words between two tiles' global counters
+
+template <bool TILE_COUNTS>
 __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(
 	const uint32_t* __restrict__ order, const ushort4* __restrict__ rect, int P, uint32_t grid_x, int64_t capacity,
 	int tile_bits, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ scan_state,
 	uint32_t* __restrict__ tile_hist /*[4][256]*/, uint32_t* __restrict__ zero_words, size_t zero_count,
-	GeomHeader* __restrict__ hdr)
+	GeomHeader* __restrict__ hdr, uint32_t* __restrict__ tile_count, int tiles, uint2* __restrict__ ranges,
+	uint32_t* __restrict__ tile_order)
 {
 	constexpr int TILE = EMIT_THREADS * EMIT_ITEMS;
-	__shared__ uint32_t s_hist[256];  // first digit of the tile ids; later digits are histogrammed by the pass before them
 	__shared__ uint32_t s_warp[EMIT_THREADS / 32];
 	__shared__ uint32_t s_prefix;
 	__shared__ uint32_t s_tile;
+	__shared__ bool s_last;
+	__shared__ uint32_t s_ph[4][256];  // !TILE_COUNTS: [0] = first digit of the tile ids.  TILE_COUNTS, last CTA: digit histograms of all passes
+	__shared__ uint32_t s_cnt[128], s_off[128];
+	__shared__ uint32_t s_tc[TILE_COUNTS ? COUNT_TILES_MAX : 1];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	pdl_trigger();
+	for (int i = tid; i < 4 * 256; i += EMIT_THREADS) (&s_ph[0][0])[i] = 0;
+	if (tid < 128) s_cnt[tid] = 0;
+	if (TILE_COUNTS) for (int i = tid; i < tiles; i += EMIT_THREADS) s_tc[i] = 0;
+	pdl_wait();
 	if (tid == 0) s_tile = atomicAdd(&hdr->scan_ticket, 1u);
-	if (tid < 256) s_hist[tid] = 0;
 	// zero the tile sort's look-back words (they are first read by the next kernel)
 	for (size_t i = (size_t)blockIdx.x * EMIT_THREADS + tid; i < zero_count; i += (size_t)gridDim.x * EMIT_THREADS) zero_words[i] = 0;
 	__syncthreads();
@@ -258,8 +277,8 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(
 	for (int k = 0; k < EMIT_ITEMS; k++) {
 		g[k] = 0; n[k] = 0; r[k] = make_ushort4(0, 0, 0, 0);
 		if (base + k < P) {
-			g[k] = order[base + k];
-			r[k] = rect[g[k]];
+			g[k] = __ldcg(order + base + k);
+			r[k] = __ldcg(rect + g[k]);
 			n[k] = (uint32_t)(r[k].z - r[k].x) * (uint32_t)(r[k].w - r[k].y);
 		}
 		sum += n[k];
@@ -293,7 +312,8 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(
 		if ((int64_t)pos < capacity) {
 			keys[pos] = key;
 			vals[pos] = val;
-			atomicAdd(&s_hist[key & m0], 1u);
+			if (TILE_COUNTS) atomicAdd(&s_tc[key], 1u);
+			else atomicAdd(&s_ph[0][key & m0], 1u);
 		}
 	};
 #pragma unroll
@@ -319,7 +339,69 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(
 		start += n[k];
 	}
 	__syncthreads();
-	if (tid < 256 && s_hist[tid]) atomicAdd(tile_hist + tid, s_hist[tid]);
+	if (!TILE_COUNTS) {
+		if (tid < 256 && s_ph[0][tid]) atomicAdd(tile_hist + tid, s_ph[0][tid]);
+		return;
+	}
+	// ---- the last CTA to get here turns the tile counts into: tile ranges (identifyTileRanges,
+	// rasterizer_impl.cu:116-138: [start,end) per tile, (0,0) for untouched tiles), the digit histograms of the
+	// tile-sort passes, and the launch order of the blend units (tile ids, longest range first; 7-bit key =
+	// position of the leading one + the next two bits of the length; order inside a bucket is arbitrary).
+	for (int i = tid; i < tiles; i += EMIT_THREADS) {
+		const uint32_t c = s_tc[i];
+		if (c) atomicAdd(tile_count + (size_t)i * COUNT_STRIDE, c);
+	}
+	__syncthreads();
+	if (tid == 0) {
+		__threadfence();  // cumulative: the CTA's REDs (observed through the barrier) are ordered before the ticket
+		s_last = atomicAdd(&hdr->emit_done, 1u) == gridDim.x - 1;
+	}
+	__syncthreads();
+	if (!s_last) return;
+	__threadfence();
+	auto key_of = [](uint32_t len) -> uint32_t {
+		if (len == 0) return 0u;
+		const int msb = 31 - __clz(len);
+		const uint32_t frac = msb >= 2 ? (len >> (msb - 2)) & 3u : (len << (2 - msb)) & 3u;
+		return min(127u, (uint32_t)(msb + 1) * 4u + frac - 3u);
+	};
+	const int passes = (tile_bits + 7) / 8;
+	uint32_t running = 0;
+	for (int t0 = 0; t0 < tiles; t0 += EMIT_THREADS) {
+		const int t = t0 + tid;
+		const uint32_t c = t < tiles ? __ldcg(tile_count + (size_t)t * COUNT_STRIDE) : 0u;
+		uint32_t incl = c;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+			if (lane >= o) incl += a;
+		}
+		__syncthreads();  // s_warp / s_prefix reuse
+		if (lane == 31) s_warp[warp] = incl;
+		__syncthreads();
+		uint32_t wp = 0, tot = 0;
+		for (int w = 0; w < EMIT_THREADS / 32; w++) {
+			if (w < warp) wp += s_warp[w];
+			tot += s_warp[w];
+		}
+		if (t < tiles) {
+			const uint32_t b = running + wp + incl - c;
+			ranges[t] = c ? make_uint2(b, b + c) : make_uint2(0u, 0u);
+			if (c) {
+				for (int p = 0; p < passes; p++) atomicAdd(&s_ph[p][((uint32_t)t >> (8 * p)) & 255u], c);
+			}
+			atomicAdd(&s_cnt[key_of(c)], 1u);
+		}
+		running += tot;
+	}
+	__syncthreads();
+	for (int i = tid; i < passes * 256; i += EMIT_THREADS) tile_hist[i] = (&s_ph[0][0])[i];
+	if (tid == 0) {
+		uint32_t run = 0;
+		for (int k = 127; k >= 0; k--) { s_off[k] = run; run += s_cnt[k]; }
+	}
+	__syncthreads();
+	for (int t = tid; t < tiles; t += EMIT_THREADS) tile_order[atomicAdd(&s_off[key_of(__ldcg(tile_count + (size_t)t * COUNT_STRIDE))], 1u)] = (uint32_t)t;
 }
 
 // K5: identifyTileRanges (rasterizer_impl.cu:116-138; `ranges` zero-initialised by the preprocess kernel, :310),
@@ -330,12 +412,14 @@ __global__ void __launch_bounds__(256) tile_ranges_schedule_kernel(
 	const uint32_t* __restrict__ tile_keys, int64_t n_max, const unsigned long long* __restrict__ n_dev,
 	uint2* __restrict__ ranges, int tiles, uint32_t* __restrict__ order, unsigned int* __restrict__ done_counter)
 {
+	pdl_trigger();
+	pdl_wait();
 	const int64_t n = load_count(n_dev, n_max);
 	for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
-		const uint32_t cur = tile_keys[idx];
+		const uint32_t cur = __ldcg(tile_keys + idx);
 		if (idx == 0) ranges[cur].x = 0;
 		else {
-			const uint32_t prev = tile_keys[idx - 1];
+			const uint32_t prev = __ldcg(tile_keys + idx - 1);
 			if (cur != prev) { ranges[prev].y = (uint32_t)idx; ranges[cur].x = (uint32_t)idx; }
 		}
 		if (idx == n - 1) ranges[cur].y = (uint32_t)n;
@@ -379,9 +463,12 @@ __global__ void __launch_bounds__(256) debug_keys_kernel(const uint32_t* __restr
 
 }  // namespace
 
+bool tile_counts_path(int tiles) { return tiles <= COUNT_TILES_MAX; }
+int tile_count_stride() { return COUNT_STRIDE; }
+
 int launch_radix_sort(uint32_t* key_a, uint32_t* key_b, uint32_t* val_a, uint32_t* val_b, int64_t n_max,
                       const unsigned long long* n_dev, int end_bit, uint32_t* hist, uint32_t* lookback,
-                      unsigned int* tickets, cudaStream_t stream) {
+                      unsigned int* tickets, cudaStream_t stream, bool hist_ready) {
 	if (n_max <= 0 || end_bit <= 0) return 0;
 	const int passes = (end_bit + 7) / 8;
 	const int items = sort_items_for(n_max);
@@ -391,13 +478,14 @@ int launch_radix_sort(uint32_t* key_a, uint32_t* key_b, uint32_t* val_a, uint32_
 		const int bits = end_bit - 8 * p < 8 ? end_bit - 8 * p : 8;
 		const bool more = p + 1 < passes;
 		const int nbits = more ? (end_bit - 8 * (p + 1) < 8 ? end_bit - 8 * (p + 1) : 8) : 1;
-		uint32_t* nh = more ? hist + 256 * (p + 1) : nullptr;  // histogram of the next pass's digit, taken while this pass reads the keys
+		// histogram of the next pass's digit, taken while this pass reads the keys (unless the caller already has all of them)
+		uint32_t* nh = (more && !hist_ready) ? hist + 256 * (p + 1) : nullptr;
 		uint32_t* lb = lookback + (size_t)p * tiles * 256;
 		if (items == SORT_ITEMS_SMALL)
-			onesweep_pass_kernel<SORT_ITEMS_SMALL><<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(
+			launch_k(PDL_SORT, onesweep_pass_kernel<SORT_ITEMS_SMALL>, dim3((unsigned)tiles), dim3(SORT_THREADS), stream,
 				ki, vi, ko, vo, n_max, n_dev, 8 * p, bits, hist + 256 * p, nh, 8 * (p + 1), nbits, lb, tickets + p);
 		else
-			onesweep_pass_kernel<SORT_ITEMS_LARGE><<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(
+			launch_k(PDL_SORT, onesweep_pass_kernel<SORT_ITEMS_LARGE>, dim3((unsigned)tiles), dim3(SORT_THREADS), stream,
 				ki, vi, ko, vo, n_max, n_dev, 8 * p, bits, hist + 256 * p, nh, 8 * (p + 1), nbits, lb, tickets + p);
 		count_launch();
 		uint32_t* t = ki; ki = ko; ko = t;
@@ -411,18 +499,25 @@ void launch_depth_order(GeomState& gs, int P, cudaStream_t stream) {
 	if (P <= 0) return;
 	// keys: key_a, values: order (identity), digit histograms gs.hist[0..3]: all written by preprocess; 4 passes -> result in (key_a, order)
 	unsigned int* tickets = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(gs.hdr) + offsetof(GeomHeader, sort_ticket));
-	launch_radix_sort(gs.key_a, gs.key_b, gs.order, gs.val_b, P, nullptr, 32, gs.hist, gs.lookback, tickets, stream);
+	launch_radix_sort(gs.key_a, gs.key_b, gs.order, gs.val_b, P, nullptr, 32, gs.hist, gs.lookback, tickets, stream, false);
 }
 
-void launch_scan_emit(const b200gs_view_t& v, GeomState& gs, BinningState& bs, int P, int64_t capacity, cudaStream_t stream) {
+void launch_scan_emit(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is, int P, int64_t capacity, cudaStream_t stream, bool chained) {
 	if (P <= 0) return;
 	const uint32_t gx = (v.width + TILE_X - 1) / TILE_X, gy = (v.height + TILE_Y - 1) / TILE_Y;
 	const int bit = (int)higher_msb(gx * gy);
 	const int64_t tiles_L = sort_tiles_for(capacity);
 	const int passes = (bit + 7) / 8;
 	const unsigned grid = (unsigned)((P + EMIT_THREADS * EMIT_ITEMS - 1) / (EMIT_THREADS * EMIT_ITEMS));
-	scan_emit_kernel<<<grid, EMIT_THREADS, 0, stream>>>(gs.order, gs.rect, P, gx, capacity, bit, bs.key_a, bs.val_a,
-		reinterpret_cast<uint32_t*>(gs.scan_state), gs.hist + 4 * 256, bs.lookback, (size_t)passes * tiles_L * 256, gs.hdr);
+	const int tiles = (int)(gx * gy);
+	if (tile_counts_path(tiles))
+		launch_impl(chained ? PDL_EMIT : 0u, scan_emit_kernel<true>, dim3(grid), dim3(EMIT_THREADS), stream, (const uint32_t*)gs.order, (const ushort4*)gs.rect, P, gx, capacity, bit,
+			bs.key_a, bs.val_a, reinterpret_cast<uint32_t*>(gs.scan_state), gs.hist + 4 * 256, bs.lookback, (size_t)passes * tiles_L * 256, gs.hdr,
+			is.tile_count, tiles, is.ranges, is.tile_order);
+	else
+		launch_impl(chained ? PDL_EMIT : 0u, scan_emit_kernel<false>, dim3(grid), dim3(EMIT_THREADS), stream, (const uint32_t*)gs.order, (const ushort4*)gs.rect, P, gx, capacity, bit,
+			bs.key_a, bs.val_a, reinterpret_cast<uint32_t*>(gs.scan_state), gs.hist + 4 * 256, bs.lookback, (size_t)passes * tiles_L * 256, gs.hdr,
+			is.tile_count, tiles, is.ranges, is.tile_order);
 	count_launch();
 }
 
@@ -432,7 +527,7 @@ void launch_tile_sort(const b200gs_view_t& v, GeomState& gs, BinningState& bs, i
 	const unsigned long long* n_dev = &gs.hdr->num_rendered;
 	unsigned int* tickets = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(gs.hdr) + offsetof(GeomHeader, sort_ticket)) + 4;
 	const int where = launch_radix_sort(bs.key_a, bs.key_b, bs.val_a, bs.val_b, capacity, n_dev, bit, gs.hist + 4 * 256,
-	                                    bs.lookback, tickets, stream);
+	                                    bs.lookback, tickets, stream, tile_counts_path((int)(gx * gy)));
 	bs.sorted_keys = where ? bs.key_b : bs.key_a;
 	bs.sorted_vals = where ? bs.val_b : bs.val_a;
 }
@@ -444,7 +539,7 @@ void launch_tile_ranges(const b200gs_view_t& v, GeomState& gs, BinningState& bs,
 	// few CTAs (grid-stride): every CTA ends with one atomic on the same counter
 	const unsigned grid = (unsigned)(n_max > 0 ? (n_max + 255) / 256 < 148 * 4 ? (n_max + 255) / 256 : 148 * 4 : 1);
 	unsigned int* counter = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(gs.hdr) + offsetof(GeomHeader, ranges_done));
-	tile_ranges_schedule_kernel<<<grid, 256, 0, stream>>>(bs.sorted_keys, n_max, n_dev, is.ranges, tiles, is.tile_order, counter);
+	launch_k(PDL_RANGES, tile_ranges_schedule_kernel, dim3(grid), dim3(256), stream, (const uint32_t*)bs.sorted_keys, n_max, n_dev, is.ranges, tiles, is.tile_order, counter);
 	count_launch();
 }
 

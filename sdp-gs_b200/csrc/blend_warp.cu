@@ -37,7 +37,7 @@ __device__ __forceinline__ Unit make_unit(const uint32_t* __restrict__ order, co
 	Unit u;
 	const unsigned lane = threadIdx.x & 31;
 	const uint32_t unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-	u.tile = order[unit >> 3];
+	u.tile = __ldca(order + (unit >> 3));
 	const int sub = unit & 7;
 	const unsigned tx = u.tile % grid_x, ty = u.tile / grid_x;
 	const unsigned bx = tx * TILE_X + (sub & 1) * 8, by = ty * TILE_Y + (sub >> 1) * 4;
@@ -48,7 +48,7 @@ __device__ __forceinline__ Unit make_unit(const uint32_t* __restrict__ order, co
 	u.pyf = (float)u.py;
 	u.pb.X0 = (float)bx; u.pb.X1 = u.pb.X0 + 7.f;
 	u.pb.Y0 = (float)by; u.pb.Y1 = u.pb.Y0 + 3.f;
-	u.range = ranges[u.tile];
+	u.range = __ldca(ranges + u.tile);
 	return u;
 }
 
@@ -70,6 +70,8 @@ __global__ void __launch_bounds__(32) blend_forward_warp_kernel(
 	__shared__ float4 s_g3[EXT ? 64 : 1];
 	const unsigned lane = threadIdx.x & 31;
 	const unsigned lt_mask = (1u << lane) - 1u;
+	pdl_trigger();
+	pdl_wait();
 	const Unit u = make_unit(order, ranges, W, H, grid_x);
 	const int n = (int)(u.range.y - u.range.x);
 	constexpr int NC = EXT ? 8 : 3;
@@ -134,13 +136,13 @@ __global__ void __launch_bounds__(32) blend_forward_warp_kernel(
 
 	auto load_id = [&](int base) -> uint32_t {
 		const int i = base + (int)lane;
-		return (i < n) ? __ldg(point_list + u.range.x + i) : NOID;
+		return (i < n) ? __ldca(point_list + u.range.x + i) : NOID;
 	};
 	auto load_geo = [&](uint32_t id, float4& g0, float4& g1) {
-		if (id != NOID) { const float4* r = rec + 4 * (size_t)id; g0 = __ldg(r); g1 = __ldg(r + 1); }
+		if (id != NOID) { const float4* r = rec + 4 * (size_t)id; g0 = __ldca(r); g1 = __ldca(r + 1); }
 	};
 	auto load_pay = [&](uint32_t id, bool keep, float4& g2, float4& g3) {
-		if (keep) { const float4* r = rec + 4 * (size_t)id; g2 = __ldg(r + 2); if (EXT) g3 = __ldg(r + 3); }
+		if (keep) { const float4* r = rec + 4 * (size_t)id; g2 = __ldca(r + 2); if (EXT) g3 = __ldca(r + 3); }
 	};
 	float4 xg0, xg1, xg2, xg3, yg0, yg1;
 	xg0 = xg1 = xg2 = xg3 = yg0 = yg1 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -225,6 +227,8 @@ __global__ void __launch_bounds__(32) blend_backward_warp_kernel(
 	__shared__ float4 s_dpix[32][2];
 	const unsigned lane = threadIdx.x & 31;
 	const unsigned gt_mask = lane == 31 ? 0u : (0xFFFFFFFFu << (lane + 1));
+	pdl_trigger();
+	pdl_wait();
 	const Unit u = make_unit(order, ranges, W, H, grid_x);
 	const size_t pix = (size_t)u.py * W + u.px, HW = (size_t)H * W;
 
@@ -344,13 +348,13 @@ __global__ void __launch_bounds__(32) blend_backward_warp_kernel(
 
 	auto load_id = [&](int base) -> uint32_t {
 		const int i = base + (int)lane;
-		return (base >= 0 && (uint32_t)i < wmax) ? __ldg(point_list + u.range.x + i) : NOID;
+		return (base >= 0 && (uint32_t)i < wmax) ? __ldca(point_list + u.range.x + i) : NOID;
 	};
 	auto load_geo = [&](uint32_t id, float4& g0, float4& g1) {
-		if (id != NOID) { const float4* r = rec + 4 * (size_t)id; g0 = __ldg(r); g1 = __ldg(r + 1); }
+		if (id != NOID) { const float4* r = rec + 4 * (size_t)id; g0 = __ldca(r); g1 = __ldca(r + 1); }
 	};
 	auto load_pay = [&](uint32_t id, bool keep, float4& g2, float4& g3) {
-		if (keep) { const float4* r = rec + 4 * (size_t)id; g2 = __ldg(r + 2); if (EXT) g3 = __ldg(r + 3); }
+		if (keep) { const float4* r = rec + 4 * (size_t)id; g2 = __ldca(r + 2); if (EXT) g3 = __ldca(r + 3); }
 	};
 	// list positions [0, wmax) back to front, 32 per round
 	const int base0 = (int)((wmax - 1) & ~31u);
@@ -418,10 +422,10 @@ void launch_blend_forward(const b200gs_view_t& v, GeomState& gs, BinningState& b
 	const int gx = (v.width + TILE_X - 1) / TILE_X, gy = (v.height + TILE_Y - 1) / TILE_Y;
 	const unsigned units = (unsigned)(gx * gy * 8);
 	if (v.extended)
-		blend_forward_warp_kernel<true><<<units, 32, 0, stream>>>(is.ranges, is.tile_order, bs.sorted_vals, gs.rec, v.width, v.height, gx,
+		launch_k(PDL_BLEND_FWD, blend_forward_warp_kernel<true>, dim3(units), dim3(32), stream, is.ranges, is.tile_order, bs.sorted_vals, gs.rec, v.width, v.height, gx,
 			v.background, is.final_T, is.n_contrib, out.color, out.depth, out.alpha, out.feature);
 	else
-		blend_forward_warp_kernel<false><<<units, 32, 0, stream>>>(is.ranges, is.tile_order, bs.sorted_vals, gs.rec, v.width, v.height, gx,
+		launch_k(PDL_BLEND_FWD, blend_forward_warp_kernel<false>, dim3(units), dim3(32), stream, is.ranges, is.tile_order, bs.sorted_vals, gs.rec, v.width, v.height, gx,
 			v.background, is.final_T, is.n_contrib, out.color, nullptr, nullptr, nullptr);
 	count_launch();
 }
@@ -432,10 +436,10 @@ void launch_blend_backward(const b200gs_view_t& v, GeomState& gs, BinningState& 
 	const int gx = (v.width + TILE_X - 1) / TILE_X, gy = (v.height + TILE_Y - 1) / TILE_Y;
 	const unsigned units = (unsigned)(gx * gy * 8);
 	if (v.extended)
-		blend_backward_warp_kernel<true><<<units, 32, 0, stream>>>(is.ranges, is.tile_order, bs.sorted_vals, gs.rec, v.width, v.height, gx,
+		launch_k_first(blend_backward_warp_kernel<true>, dim3(units), dim3(32), stream, is.ranges, is.tile_order, bs.sorted_vals, gs.rec, v.width, v.height, gx,
 			v.background, is.final_T, is.n_contrib, gout.dL_dcolor, gout.dL_ddepth, gout.dL_dalpha, gout.dL_dfeature, grec);
 	else
-		blend_backward_warp_kernel<false><<<units, 32, 0, stream>>>(is.ranges, is.tile_order, bs.sorted_vals, gs.rec, v.width, v.height, gx,
+		launch_k_first(blend_backward_warp_kernel<false>, dim3(units), dim3(32), stream, is.ranges, is.tile_order, bs.sorted_vals, gs.rec, v.width, v.height, gx,
 			v.background, is.final_T, is.n_contrib, gout.dL_dcolor, nullptr, nullptr, nullptr, grec);
 	count_launch();
 }

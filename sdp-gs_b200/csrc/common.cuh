@@ -25,7 +25,8 @@ struct GeomHeader {  // first 256 bytes of the geom workspace
 	unsigned int scan_ticket;         // dynamic tile id allocator for the look-back scan
 	unsigned int sort_ticket[8];      // one per radix pass (4 depth passes + up to 4 tile passes)
 	unsigned int ranges_done;         // CTAs of the tile-ranges kernel that have finished (last one builds the blend schedule)
-	unsigned int pad[51];
+	unsigned int emit_done;           // CTAs of scan_emit that have finished (last one turns tile counts into ranges + schedule)
+	unsigned int pad[50];
 };
 static_assert(sizeof(GeomHeader) == 256, "header size");
 
@@ -50,6 +51,7 @@ struct ImageState {
 	uint32_t* n_contrib;   // u32[N]
 	uint2* ranges;         // [tiles]
 	uint32_t* tile_order;  // [tiles] tile ids, heaviest (longest range) first: launch order of the blend units
+	uint32_t* tile_count;  // [tiles] instances per tile, counted while they are emitted (zeroed by the preprocess kernel)
 	size_t bytes;
 };
 
@@ -96,9 +98,12 @@ void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, u
 // holds the result (0: a, 1: b).
 int launch_radix_sort(uint32_t* key_a, uint32_t* key_b, uint32_t* val_a, uint32_t* val_b, int64_t n_max,
                       const unsigned long long* n_dev, int end_bit, uint32_t* hist /*[passes][256]*/,
-                      uint32_t* lookback, unsigned int* tickets, cudaStream_t stream);
+                      uint32_t* lookback, unsigned int* tickets, cudaStream_t stream, bool hist_ready = false);
+bool tile_counts_path(int tiles);  // scan_emit also produces tile ranges + blend schedule (small tile grids)
+int tile_count_stride();
 void launch_depth_order(GeomState& gs, int P, cudaStream_t stream);                     // stable sort of Gaussian ids by depth bits
-void launch_scan_emit(const b200gs_view_t& v, GeomState& gs, BinningState& bs, int P, int64_t capacity, cudaStream_t stream);
+void launch_scan_emit(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is, int P, int64_t capacity, cudaStream_t stream,
+                      bool chained /* the previous kernel in the stream is our depth sort */);
 void launch_tile_sort(const b200gs_view_t& v, GeomState& gs, BinningState& bs, int64_t capacity, cudaStream_t stream);
 void launch_tile_ranges(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is, int64_t capacity, cudaStream_t stream);
 void launch_debug_keys(const b200gs_view_t& v, GeomState& gs, BinningState& bs, uint64_t* keys_out, int64_t L,
@@ -111,6 +116,46 @@ void launch_blend_backward(const b200gs_view_t& v, GeomState& gs, BinningState& 
 
 // ---- device helpers ----
 #ifdef __CUDACC__
+// Programmatic dependent launch (sm_90+): every kernel of the chain is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization (launch_k below).  pdl_trigger() lets the NEXT kernel's CTAs
+// become resident while this one is still running; pdl_wait() blocks until every earlier kernel in the stream
+// has completed and its writes are visible.  Rule used throughout: trigger first, touch only shared memory
+// and registers, then wait before the first global access.  Without the launch attribute both are no-ops.
+// Data produced by an earlier kernel of the chain must NOT be read through the non-coherent path (__ldg /
+// `const __restrict__` -> LDG.E.CONSTANT): a programmatically launched grid is already alive while its producer
+// writes, so "read-only for the lifetime of the kernel" does not hold and stale lines were observed (wrong sort
+// output).  Such loads use __ldcg (streamed once) or __ldca (re-used within an SM) explicitly.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+unsigned pdl_mask();  // B200GS_PDL=<bitmask of launch sites> (0 turns programmatic launches off; A/B measurements)
+enum PdlSite { PDL_SORT = 1, PDL_EMIT = 2, PDL_RANGES = 4, PDL_BLEND_FWD = 8, PDL_PRE_BWD = 16 };
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_impl(unsigned site, void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args&&... args) {
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = grid;
+	cfg.blockDim = block;
+	cfg.dynamicSmemBytes = 0;
+	cfg.stream = stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = (site & pdl_mask()) ? 1 : 0;
+	return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// kernel whose predecessor in the stream is one of OUR kernels (all of which execute pdl_wait): programmatic launch
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(unsigned site, void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args&&... args) {
+	return launch_impl(site, kernel, grid, block, stream, static_cast<Args&&>(args)...);
+}
+// first kernel of a chain: its predecessor is a memset / copy / foreign kernel, so it is launched with full stream
+// ordering (measured: a programmatic launch behind cudaMemsetAsync may start before the memset has landed)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k_first(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args&&... args) {
+	return launch_impl(0u, kernel, grid, block, stream, static_cast<Args&&>(args)...);
+}
 // a0*b0 + a1*b1 + a2*b2 with the rounding sequence the reference's sm_100a build executes
 // (FMUL, FFMA, FFMA); pinned with .rn intrinsics so neither cicc nor ptxas may re-associate.
 __device__ __forceinline__ float dot3_pinned(float a0, float b0, float a1, float b1, float a2, float b2) {

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(
 	int W, int H, float tan_fovx, float tan_fovy, float focal_x, float focal_y, int extended, int prefiltered,
 	int32_t* __restrict__ radii, float* __restrict__ depths, ushort4* __restrict__ rects, float4* __restrict__ rec,
 	uint8_t* __restrict__ clamped, uint32_t* __restrict__ sort_keys, uint32_t* __restrict__ sort_vals,
-	uint32_t* __restrict__ depth_hist /*[256]: first digit; later digits are histogrammed by the pass before them*/, uint2* __restrict__ ranges, int tiles, GeomHeader* __restrict__ hdr,
+	uint32_t* __restrict__ depth_hist /*[256]: first digit; later digits are histogrammed by the pass before them*/, uint2* __restrict__ ranges, uint32_t* __restrict__ tile_count, int count_stride, int tiles, GeomHeader* __restrict__ hdr,
 	int tma_ok)
 {
 	// digit histograms of the depth-sort keys (consumed by the four radix passes that follow)
@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(
 	__shared__ __align__(128) float4 s_rec[PRE_THREADS * 4];    // outgoing splat records
 	__shared__ __align__(8) uint64_t s_bar;
 	const int li = threadIdx.x;
+	pdl_trigger();
 	const size_t base = (size_t)blockIdx.x * PRE_THREADS;
 	const int cnt = (int)min((size_t)PRE_THREADS, (size_t)P - base);
 	const bool sh_staged = shs != nullptr && M <= 16;
@@ -178,8 +179,9 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(
 	for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
 	if (threadIdx.x == 0) s_instances = 0ull;
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	// tile ranges start at (0,0) for every tile (cudaMemset in the reference, rasterizer_impl.cu:310)
-	for (int t = idx; t < tiles; t += gridDim.x * blockDim.x) ranges[t] = make_uint2(0u, 0u);
+	pdl_wait();  // the parameters may have been written by the kernel just before this one (optimizer step)
+	// tile ranges start at (0,0) for every tile (cudaMemset in the reference, rasterizer_impl.cu:310); per-tile instance counters at 0
+	for (int t = idx; t < tiles; t += gridDim.x * blockDim.x) { ranges[t] = make_uint2(0u, 0u); tile_count[(size_t)t * count_stride] = 0u; }
 	__syncthreads();
 	if (li == 0 && st.tma) {
 		uint32_t tx = PRE_THREADS * 4 * (3 + 1);
@@ -388,6 +390,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_backward_kernel(
 	__shared__ __align__(16) float s_oc[PRE_THREADS * 3];       // dL/dcolors out
 	__shared__ __align__(8) uint64_t s_bar;
 	const int li = threadIdx.x;
+	pdl_trigger();
 	const size_t base = (size_t)blockIdx.x * PRE_THREADS;
 	const int cnt = (int)min((size_t)PRE_THREADS, (size_t)P - base);
 	const bool sh_staged = shs != nullptr && M <= 16;
@@ -395,6 +398,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_backward_kernel(
 	Stage st;
 	st.bar = &s_bar; st.tma = full; st.cnt = cnt; st.tid = li;
 	if (li == 0 && full) mbar_init(&s_bar, 1);
+	pdl_wait();
 	__syncthreads();
 	if (li == 0 && full) {
 		uint32_t tx = PRE_THREADS * 4 * (16 + 3);
@@ -424,7 +428,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_backward_kernel(
 #pragma unroll
 	for (int k = 0; k < 16; k++) shw[k] = 0.f;
 	float dRGB[3] = {0.f, 0.f, 0.f};
-	if (idx < P && radii[idx] > 0) {
+	if (idx < P && __ldcg(radii + idx) > 0) {
 	ViewConsts vc;
 	load_view(vc, viewmatrix, projmatrix, campos);
 	const float* vm = vc.view;
@@ -534,7 +538,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_backward_kernel(
 	if (shs == nullptr) {
 		o_col[0] = dRGB[0]; o_col[1] = dRGB[1]; o_col[2] = dRGB[2];
 	} else {
-		const unsigned cl = clamped[idx];
+		const unsigned cl = __ldcg(clamped + idx);
 		dRGB[0] *= (cl & 1u) ? 0.f : 1.f; dRGB[1] *= (cl & 2u) ? 0.f : 1.f; dRGB[2] *= (cl & 4u) ? 0.f : 1.f;
 		const float dox = mx - vc.campos[0], doy = my - vc.campos[1], doz = mz - vc.campos[2];
 		const float ilen = 1.0f / sqrtf(dox * dox + doy * doy + doz * doz);
@@ -723,11 +727,11 @@ void launch_preprocess_forward(const b200gs_view_t& v, const b200gs_gaussians_t&
 	const int tma_ok = al16(g.means3D) && al16(g.scales) && al16(g.rotations) && al16(g.opacities) && al16(g.shs) &&
 	                   al16(g.cov3D_precomp) && al16(g.colors_precomp) && al16(g.language_feature_precomp) &&
 	                   al16(g.shs_language) && al16(g.confidence);
-	preprocess_forward_kernel<<<(P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, stream>>>(
+	launch_k_first(preprocess_forward_kernel, dim3((P + PRE_THREADS - 1) / PRE_THREADS), dim3(PRE_THREADS), stream,
 		P, v.sh_degree, v.sh_coeffs, g.means3D, g.scales, v.scale_modifier, g.rotations, g.opacities, g.shs,
 		g.cov3D_precomp, g.colors_precomp, g.language_feature_precomp, g.shs_language, g.confidence,
 		v.viewmatrix, v.projmatrix, v.campos, v.width, v.height, v.tan_fovx, v.tan_fovy, focal_x, focal_y,
-		v.extended, v.prefiltered, radii, gs.depths, gs.rect, gs.rec, gs.clamped, gs.key_a, gs.order, gs.hist, is.ranges,
+		v.extended, v.prefiltered, radii, gs.depths, gs.rect, gs.rec, gs.clamped, gs.key_a, gs.order, gs.hist, is.ranges, is.tile_count, tile_count_stride(),
 		((v.width + TILE_X - 1) / TILE_X) * ((v.height + TILE_Y - 1) / TILE_Y), gs.hdr, tma_ok);
 	count_launch();
 }
@@ -742,7 +746,7 @@ void launch_preprocess_backward(const b200gs_view_t& v, const b200gs_gaussians_t
 	                   al16(g.shs_language) && al16(g.confidence) && al16(grec) && al16(gr.dL_dmeans3D) && al16(gr.dL_dmeans2D) &&
 	                   al16(gr.dL_dshs) && al16(gr.dL_dcolors) && al16(gr.dL_dscales) && al16(gr.dL_dcov3D) && al16(gr.dL_dfeatures) &&
 	                   al16(gr.dL_dshs_language);
-	preprocess_backward_kernel<<<(P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, stream>>>(
+	launch_k(PDL_PRE_BWD, preprocess_backward_kernel, dim3((P + PRE_THREADS - 1) / PRE_THREADS), dim3(PRE_THREADS), stream,
 		P, v.sh_degree, v.sh_coeffs, g.means3D, radii, g.shs, gs.clamped, g.scales, g.rotations, v.scale_modifier,
 		g.cov3D_precomp, g.language_feature_precomp, g.shs_language, g.confidence, v.viewmatrix, v.projmatrix,
 		v.campos, focal_x, focal_y, v.tan_fovx, v.tan_fovy, v.extended, reinterpret_cast<const float4*>(grec),
