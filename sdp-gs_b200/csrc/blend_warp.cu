@@ -19,6 +19,8 @@
 //     Gaussian (pixel moments of the pair weights left in shared memory by the first phase), so there
 //     is no cross-lane reduction and no per-pair atomic: four 16-byte vector reductions per
 //     (block, Gaussian) replace the reference's 9 float atomics per blended pair.
+#include <cstdlib>
+#include <cstring>
 #include "common.cuh"
 #include "blend_common.cuh"
 
@@ -400,13 +402,18 @@ __global__ void __launch_bounds__(32) blend_backward_warp_kernel(
 	}
 }
 
-bool use_tile_cta_path() {
-	static int v = -1;
-	if (v < 0) {
+// B200GS_BLEND selects the blend kernels for A/B measurements: "pipe" (default; blend_pipe.cu), "warp" (this file),
+// "tile" (CTA per tile, blend.cu).  Optional suffixes pick per direction, e.g. B200GS_BLEND=pipe,warp = forward pipe, backward warp.
+int blend_variant(int dir) {
+	static int v[2] = {-1, -1};
+	if (v[0] < 0) {
 		const char* e = getenv("B200GS_BLEND");
-		v = (e && e[0] == 't') ? 1 : 0;  // B200GS_BLEND=tile selects the CTA-per-tile kernels of blend.cu (A/B measurements)
+		auto parse = [](const char* s) { return (!s || !*s || *s == 'p') ? 2 : (*s == 't' ? 1 : 0); };
+		v[0] = parse(e);
+		const char* c = e ? strchr(e, ',') : nullptr;
+		v[1] = c ? parse(c + 1) : v[0];
 	}
-	return v == 1;
+	return v[dir];
 }
 
 }  // namespace
@@ -416,9 +423,15 @@ void launch_blend_forward_tile(const b200gs_view_t& v, GeomState& gs, BinningSta
 void launch_blend_backward_tile(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
                                 const b200gs_grad_outputs_t& gout, float* grec, cudaStream_t stream);
 
+void launch_blend_forward_pipe(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
+                               const b200gs_outputs_t& out, cudaStream_t stream);
+void launch_blend_backward_pipe(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
+                                const b200gs_grad_outputs_t& gout, float* grec, cudaStream_t stream);
+
 void launch_blend_forward(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
                           const b200gs_outputs_t& out, cudaStream_t stream) {
-	if (use_tile_cta_path()) return launch_blend_forward_tile(v, gs, bs, is, out, stream);
+	if (blend_variant(0) == 2) return launch_blend_forward_pipe(v, gs, bs, is, out, stream);
+	if (blend_variant(0) == 1) return launch_blend_forward_tile(v, gs, bs, is, out, stream);
 	const int gx = (v.width + TILE_X - 1) / TILE_X, gy = (v.height + TILE_Y - 1) / TILE_Y;
 	const unsigned units = (unsigned)(gx * gy * 8);
 	if (v.extended)
@@ -432,7 +445,8 @@ void launch_blend_forward(const b200gs_view_t& v, GeomState& gs, BinningState& b
 
 void launch_blend_backward(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
                            const b200gs_grad_outputs_t& gout, float* grec, cudaStream_t stream) {
-	if (use_tile_cta_path()) return launch_blend_backward_tile(v, gs, bs, is, gout, grec, stream);
+	if (blend_variant(1) == 2) return launch_blend_backward_pipe(v, gs, bs, is, gout, grec, stream);
+	if (blend_variant(1) == 1) return launch_blend_backward_tile(v, gs, bs, is, gout, grec, stream);
 	const int gx = (v.width + TILE_X - 1) / TILE_X, gy = (v.height + TILE_Y - 1) / TILE_Y;
 	const unsigned units = (unsigned)(gx * gy * 8);
 	if (v.extended)
