@@ -234,14 +234,11 @@ __global__ void __launch_bounds__(32) blend_backward_warp_kernel(
 	const Unit u = make_unit(order, ranges, W, H, grid_x);
 	const size_t pix = (size_t)u.py * W + u.px, HW = (size_t)H * W;
 
+	// everything the unit needs from the image planes is requested at once, ahead of the wmax == 0 exit test (ncu: 23 % of
+	// the kernel's warp-time was spent in this prologue, serialised as n_contrib -> cotangents -> ids -> records)
 	const float T_final = u.inside ? final_T[pix] : 0.f;
 	float T = T_final;
 	const uint32_t last_contributor = u.inside ? n_contrib[pix] : 0u;
-	uint32_t wmax = last_contributor;
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xFFFFFFFFu, wmax, o));
-	if (wmax == 0) return;  // nothing was blended into this block
-
 	float dpix[NC];
 #pragma unroll
 	for (int ch = 0; ch < NC; ch++) dpix[ch] = 0.f;
@@ -253,6 +250,11 @@ __global__ void __launch_bounds__(32) blend_backward_warp_kernel(
 			if (dL_dfeat) { dpix[5] = dL_dfeat[pix]; dpix[6] = dL_dfeat[HW + pix]; dpix[7] = dL_dfeat[2 * HW + pix]; }
 		}
 	}
+	uint32_t wmax = last_contributor;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xFFFFFFFFu, wmax, o));
+	if (wmax == 0) return;  // nothing was blended into this block
+
 	// cotangents of the channels that own a per-Gaussian gradient: r,g,b,z | f0,f1,f2
 	s_dpix[lane][0] = make_float4(dpix[0], dpix[1], dpix[2], EXT ? dpix[3] : 0.f);
 	s_dpix[lane][1] = EXT ? make_float4(dpix[5], dpix[6], dpix[7], 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -402,16 +404,17 @@ __global__ void __launch_bounds__(32) blend_backward_warp_kernel(
 	}
 }
 
-// B200GS_BLEND selects the blend kernels for A/B measurements: "pipe" (default; blend_pipe.cu), "warp" (this file),
-// "tile" (CTA per tile, blend.cu).  Optional suffixes pick per direction, e.g. B200GS_BLEND=pipe,warp = forward pipe, backward warp.
+// B200GS_BLEND selects the blend kernels for A/B measurements: "warp" (this file), "async" (blend_async.cu),
+// "pipe" (blend_pipe.cu), "tile" (CTA per tile, blend.cu).  Optional suffixes pick per direction, e.g. B200GS_BLEND=pipe,warp = forward pipe, backward warp.
 int blend_variant(int dir) {
 	static int v[2] = {-1, -1};
 	if (v[0] < 0) {
 		const char* e = getenv("B200GS_BLEND");
-		auto parse = [](const char* s) { return (!s || !*s || *s == 'p') ? 2 : (*s == 't' ? 1 : 0); };
-		v[0] = parse(e);
+		auto parse = [](const char* s, int dflt) { return (!s || !*s) ? dflt : (*s == 'a' ? 3 : (*s == 'p' ? 2 : (*s == 't' ? 1 : 0))); };
+		// defaults (measured, profiles/): forward = async list prefetch, backward = warp-autonomous register pipeline
 		const char* c = e ? strchr(e, ',') : nullptr;
-		v[1] = c ? parse(c + 1) : v[0];
+		v[1] = c ? parse(c + 1, 0) : parse(e, 0);
+		v[0] = parse(e, 3);
 	}
 	return v[dir];
 }
@@ -425,11 +428,14 @@ void launch_blend_backward_tile(const b200gs_view_t& v, GeomState& gs, BinningSt
 
 void launch_blend_forward_pipe(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
                                const b200gs_outputs_t& out, cudaStream_t stream);
+void launch_blend_forward_async(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
+                                const b200gs_outputs_t& out, cudaStream_t stream);
 void launch_blend_backward_pipe(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
                                 const b200gs_grad_outputs_t& gout, float* grec, cudaStream_t stream);
 
 void launch_blend_forward(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
                           const b200gs_outputs_t& out, cudaStream_t stream) {
+	if (blend_variant(0) == 3) return launch_blend_forward_async(v, gs, bs, is, out, stream);
 	if (blend_variant(0) == 2) return launch_blend_forward_pipe(v, gs, bs, is, out, stream);
 	if (blend_variant(0) == 1) return launch_blend_forward_tile(v, gs, bs, is, out, stream);
 	const int gx = (v.width + TILE_X - 1) / TILE_X, gy = (v.height + TILE_Y - 1) / TILE_Y;
