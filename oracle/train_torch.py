@@ -1,0 +1,93 @@
+"""ORACLE -- TEST INFRASTRUCTURE, NOT PRODUCT.
+
+Plain-PyTorch restatement of the torch-side operations of one SDP-GS training iteration, used (a) by tests/ as
+the checker of the fused kernels of include/b200gs_train.h and (b) by `bench.py --impl reference` as the
+reference's own (stock torch) code path around its CUDA rasterizer.  Each function cites what it follows:
+
+  l1_loss, ssim            utils/loss_utils.py:119-163 (11x11 window, sigma 1.5, F.conv2d groups=C, zero padding)
+  pearson_corrcoef         torchmetrics.functional.pearson_corrcoef as called at train.py:126-129
+                           (torchmetrics is not in this image: restated from its published definition
+                            r = cov(x, y) / sqrt(var(x) var(y)), clamped to [-1, 1])
+  depth_loss               train.py:115-131
+  activations              scene/gaussian_model.py:44-57 (exp, sigmoid, torch.nn.functional.normalize)
+  make_optimizer           scene/gaussian_model.py:228-267 (torch.optim.Adam(lr=0, eps=1e-15), 7 groups)
+  expon lr                 utils/general_utils.py:get_expon_lr_func
+"""
+from math import exp
+
+import torch
+import torch.nn.functional as F
+
+
+def l1_loss(network_output, gt):
+    return torch.abs((network_output - gt)).mean()
+
+
+def _gaussian(window_size, sigma):
+    gauss = torch.Tensor([exp(-(x - window_size // 2) ** 2 / float(2 * sigma ** 2)) for x in range(window_size)])
+    return gauss / gauss.sum()
+
+
+def _create_window(window_size, channel):
+    w1 = _gaussian(window_size, 1.5).unsqueeze(1)
+    w2 = w1.mm(w1.t()).float().unsqueeze(0).unsqueeze(0)
+    return w2.expand(channel, 1, window_size, window_size).contiguous()
+
+
+def ssim(img1, img2, window_size=11):
+    channel = img1.size(-3)
+    window = _create_window(window_size, channel).to(img1.device).type_as(img1)
+    pad = window_size // 2
+    mu1 = F.conv2d(img1, window, padding=pad, groups=channel)
+    mu2 = F.conv2d(img2, window, padding=pad, groups=channel)
+    mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+    sigma1_sq = F.conv2d(img1 * img1, window, padding=pad, groups=channel) - mu1_sq
+    sigma2_sq = F.conv2d(img2 * img2, window, padding=pad, groups=channel) - mu2_sq
+    sigma12 = F.conv2d(img1 * img2, window, padding=pad, groups=channel) - mu1_mu2
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    ssim_map = ((2 * mu1_mu2 + C1) * (2 * sigma12 + C2)) / ((mu1_sq + mu2_sq + C1) * (sigma1_sq + sigma2_sq + C2))
+    return ssim_map.mean()
+
+
+def pearson_corrcoef(x, y):
+    x, y = x.reshape(-1), y.reshape(-1)
+    xm, ym = x - x.mean(), y - y.mean()
+    r = (xm * ym).sum() / torch.sqrt((xm * xm).sum() * (ym * ym).sum())
+    return torch.clamp(r, -1.0, 1.0)
+
+
+def depth_loss(depth, depth_mono):
+    d1, m1 = depth.reshape(-1, 1), depth_mono.reshape(-1, 1)
+    return torch.min(1 - pearson_corrcoef(m1, d1), 1 - pearson_corrcoef(1 / (-m1 + 200), d1))
+
+
+def total_loss(image, gt, depth, depth_mono, lambda_dssim, depth_weight):
+    Ll1 = l1_loss(image, gt)
+    S = ssim(image, gt)
+    dl = depth_loss(depth, depth_mono)
+    return (1.0 - lambda_dssim) * Ll1 + lambda_dssim * (1.0 - S) + depth_weight * dl, Ll1, S, depth_weight * dl
+
+
+def activate(raw):
+    """raw: dict of leaf tensors xyz, f_dc [P,1,3], f_rest [P,15,3], opacity, scaling, rotation, feature."""
+    return dict(xyz=raw["xyz"], shs=torch.cat((raw["f_dc"], raw["f_rest"]), dim=1), opacity=torch.sigmoid(raw["opacity"]),
+                scaling=torch.exp(raw["scaling"]), rotation=F.normalize(raw["rotation"]), feature=raw["feature"])
+
+
+def make_optimizer(raw, hp):
+    groups = [
+        {"params": [raw["feature"]], "lr": hp["language_feature_lr"], "name": "language_feature"},
+        {"params": [raw["f_dc"]], "lr": hp["feature_lr"], "name": "f_dc"},
+        {"params": [raw["f_rest"]], "lr": hp["feature_lr"] / 20.0, "name": "f_rest"},
+        {"params": [raw["xyz"]], "lr": hp["position_lr_init"] * hp["spatial_lr_scale"], "name": "xyz"},
+        {"params": [raw["opacity"]], "lr": hp["opacity_lr"], "name": "opacity"},
+        {"params": [raw["scaling"]], "lr": hp["scaling_lr"], "name": "scaling"},
+        {"params": [raw["rotation"]], "lr": hp["rotation_lr"], "name": "rotation"},
+    ]
+    return torch.optim.Adam(groups, lr=0.0, eps=1e-15)
+
+
+def set_xyz_lr(optimizer, lr):
+    for g in optimizer.param_groups:
+        if g["name"] == "xyz":
+            g["lr"] = lr

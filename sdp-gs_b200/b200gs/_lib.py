@@ -56,6 +56,27 @@ class Grads(C.Structure):
                 ("dL_dshs_language", C.c_void_p), ("scratch", C.c_void_p)]
 
 
+class HParams(C.Structure):  # include/b200gs_train.h: b200gs_hparams_t (64 bytes, lives in device memory)
+    _fields_ = [("step", C.c_float), ("lr_xyz", C.c_float), ("lr_f_dc", C.c_float), ("lr_f_rest", C.c_float),
+                ("lr_opacity", C.c_float), ("lr_scaling", C.c_float), ("lr_rotation", C.c_float), ("lr_feature", C.c_float),
+                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("lambda_dssim", C.c_float),
+                ("depth_weight", C.c_float), ("pad", C.c_float * 3)]
+
+
+_PS_GROUPS = ("xyz", "shs", "opacity", "scaling", "rotation", "feature")
+
+
+class ParamState(C.Structure):  # b200gs_param_state_t
+    _fields_ = ([("P", C.c_int32)]
+                + [(f"{pre}{g}", C.c_void_p) for g in _PS_GROUPS for pre in ("", "m_", "v_", "g_")]
+                + [("opacity_act", C.c_void_p), ("scaling_act", C.c_void_p), ("rotation_act", C.c_void_p),
+                   ("g_means2D", C.c_void_p), ("radii", C.c_void_p), ("xyz_gradient_accum", C.c_void_p),
+                   ("denom", C.c_void_p), ("max_radii2D", C.c_void_p)])
+
+
+TRAIN_EXPORTS = ["b200gs_param_step", "b200gs_photometric_loss", "b200gs_photometric_scratch_bytes",
+                 "b200gs_depth_pearson_loss", "b200gs_hparams_advance"]
+
 EXPORTS = [
     "b200gs_version", "b200gs_last_error", "b200gs_geom_bytes", "b200gs_image_bytes", "b200gs_binning_bytes",
     "b200gs_scratch_bytes", "b200gs_forward_preprocess", "b200gs_forward_render", "b200gs_forward",
@@ -71,7 +92,7 @@ def _load():
             f"{LIB_PATH} not found: build it with `make -C sdp-gs_b200/csrc` (or __graft_entry__.build()). "
             "b200gs has no CPU / PyTorch fallback.")
     lib = C.CDLL(LIB_PATH)
-    for name in EXPORTS:
+    for name in EXPORTS + TRAIN_EXPORTS:
         if not hasattr(lib, name):
             raise ImportError(f"{LIB_PATH} does not export {name}")
     lib.b200gs_last_error.restype = C.c_char_p
@@ -96,6 +117,15 @@ def _load():
     lib.b200gs_abi_sizes.argtypes = [P(C.c_int64)]
     lib.b200gs_profile_enable.argtypes = [C.c_int32]
     lib.b200gs_profile_read.argtypes = [P(C.c_double), P(C.c_int64), C.c_int32]
+    lib.b200gs_param_step.argtypes = [P(ParamState), C.c_void_p, C.c_int32, C.c_void_p]
+    lib.b200gs_photometric_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.b200gs_photometric_scratch_bytes.argtypes = [C.c_int32, C.c_int32]
+    lib.b200gs_photometric_scratch_bytes.restype = C.c_size_t
+    lib.b200gs_depth_pearson_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p]
+    lib.b200gs_hparams_advance.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    assert C.sizeof(HParams) == 64
     sizes = (C.c_int64 * 6)()
     lib.b200gs_abi_sizes(sizes)
     mine = [C.sizeof(t) for t in (View, Gaussians, Outputs, Workspace, GradOutputs, Grads)]

@@ -1,0 +1,221 @@
+"""Device-resident core of one SDP-GS training iteration (train.py:93-231), built on the rasterizer:
+
+    render (b200gs_forward) -> L1+SSIM and Pearson-depth losses with their gradients (b200gs_photometric_loss,
+    b200gs_depth_pearson_loss) -> rasterizer backward (b200gs_backward) -> [image-parallel: one all-reduce of the
+    fused gradient buffer] -> activation backward + Adam + re-activation + densification statistics
+    (b200gs_param_step)
+
+Everything runs on fixed device buffers, so a whole iteration is ONE CUDA-graph replay per view (two when an
+all-reduce sits in the middle).  Per-step scalars (Adam step count, the position learning-rate schedule of
+utils/general_utils.py:get_expon_lr_func, loss weights) live in a 64-byte device block that the last kernel of the
+iteration advances (b200gs_hparams_advance), so the host is never in the loop.
+
+Parameter groups, learning rates and Adam settings follow scene/gaussian_model.py:215-267 (eps 1e-15; f_rest at
+feature_lr / 20); activations follow scene/gaussian_model.py:44-57 (exp / sigmoid / normalize); the feature head is
+rendered the way gaussian_renderer/__init__.py:280-287 does it (normalised degree-0 SH), inside the kernel.
+Not covered here (torch code of the reference keeps working on the same tensors): the segment-wise feature
+losses, pseudo-view sampling, densify_and_prune (the statistics it needs are maintained).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import parallel
+from . import rasterizer as rz
+from ._lib import HParams, ParamState, check, lib
+
+DEFAULTS = dict(  # arguments/__init__.py:75-101
+    position_lr_init=0.00016, position_lr_final=0.0000016, position_lr_delay_mult=0.01, position_lr_max_steps=30_000,
+    feature_lr=0.0025, opacity_lr=0.05, scaling_lr=0.005, rotation_lr=0.001, language_feature_lr=0.013,
+    lambda_dssim=0.2, depth_weight=0.05, spatial_lr_scale=1.0, beta1=0.9, beta2=0.999, eps=1e-15)
+
+
+def expon_lr(step, lr_init, lr_final, lr_delay_steps=0, lr_delay_mult=1.0, max_steps=1000000):
+    """utils/general_utils.py:get_expon_lr_func"""
+    if step < 0 or (lr_init == 0.0 and lr_final == 0.0):
+        return 0.0
+    if lr_delay_steps > 0:
+        delay_rate = lr_delay_mult + (1 - lr_delay_mult) * math.sin(0.5 * math.pi * min(max(step / lr_delay_steps, 0), 1))
+    else:
+        delay_rate = 1.0
+    t = min(max(step / max_steps, 0), 1)
+    return delay_rate * math.exp(math.log(lr_init) * (1 - t) + math.log(lr_final) * t)
+
+
+class GaussianTrainer:
+    def __init__(self, *, xyz, shs, opacity_raw, scaling_raw, rotation_raw, feature, cameras, gt_images, depth_mono,
+                 device, capacity, sh_degree=3, background=None, hparams=None, settings_fn=None):
+        dev = torch.device(device)
+        self.dev = dev
+        f32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32) if isinstance(a, np.ndarray) else a,
+                                        dtype=torch.float32).to(dev).contiguous()
+        self.hp = dict(DEFAULTS)
+        self.hp.update(hparams or {})
+        P = self.P = int(xyz.shape[0])
+        # raw parameters: one flat allocation of P*62 floats, Adam moments alike
+        self.widths = dict(xyz=3, shs=48, opacity=1, scaling=3, rotation=4, feature=3)
+        self.raw_flat = torch.zeros((P * 62,), dtype=torch.float32, device=dev)
+        self.m_flat = torch.zeros_like(self.raw_flat)
+        self.v_flat = torch.zeros_like(self.raw_flat)
+        self.raw, self.m, self.v = {}, {}, {}
+        c = 0
+        for k, w in self.widths.items():
+            for store, flat in ((self.raw, self.raw_flat), (self.m, self.m_flat), (self.v, self.v_flat)):
+                store[k] = flat[c * P:(c + w) * P].view(P, w)
+            c += w
+        self.raw["xyz"].copy_(f32(xyz)); self.raw["shs"].copy_(f32(shs).reshape(P, 48))
+        self.raw["opacity"].copy_(f32(opacity_raw).reshape(P, 1)); self.raw["scaling"].copy_(f32(scaling_raw))
+        self.raw["rotation"].copy_(f32(rotation_raw)); self.raw["feature"].copy_(f32(feature))
+        self.act = dict(opacity=torch.empty((P, 1), dtype=torch.float32, device=dev),
+                        scaling=torch.empty((P, 3), dtype=torch.float32, device=dev),
+                        rotation=torch.empty((P, 4), dtype=torch.float32, device=dev))
+        self.bucket = parallel.FusedGradBuffer(P, dev)
+        self.g_means2D = torch.zeros((P, 3), dtype=torch.float32, device=dev)
+        self.cameras = list(cameras)
+        self.gt = [f32(g) for g in gt_images]
+        self.mono = [f32(d).reshape(-1) for d in depth_mono]
+        self.bg = f32(background) if background is not None else torch.zeros(3, device=dev)
+        self.sh_degree = sh_degree
+        H, W = int(self.cameras[0].height), int(self.cameras[0].width)
+        self.H, self.W = H, W
+        self.hp_dev = torch.zeros((16,), dtype=torch.float32, device=dev)
+        self.accum = torch.zeros((4 + 16,), dtype=torch.float64, device=dev)
+        self.loss = torch.zeros((4,), dtype=torch.float64, device=dev)
+        self.scratch = torch.empty((lib.b200gs_photometric_scratch_bytes(W, H) // 4,), dtype=torch.float32, device=dev)
+        self.iteration = 0
+        self.set_hparams(step=1)
+        self._refresh_activations()
+
+        settings_fn = settings_fn or self._default_settings
+        grads_out = dict(means3D=self.bucket.segment("xyz"), shs=self.bucket.segment("shs"), opacities=self.bucket.segment("opacity"),
+                         scales=self.bucket.segment("scaling"), rotations=self.bucket.segment("rotation"),
+                         shs_language=self.bucket.segment("language_feature"), means2D=self.g_means2D)
+        self.sessions = []
+        for cam in self.cameras:
+            s = rz.RasterSession(settings_fn(cam), means3D=self.raw["xyz"], opacities=self.act["opacity"],
+                                 shs=self.raw["shs"].view(P, 16, 3), scales=self.act["scaling"], rotations=self.act["rotation"],
+                                 shs_language=self.raw["feature"], extended=True, capacity=capacity, grads_out=grads_out)
+            self.sessions.append(s)
+        self.graphs = None
+
+    # ------------------------------------------------------------------ pieces
+    def _default_settings(self, cam):
+        from diff_gaussian_rasterization import GaussianRasterizationSettings as S
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.dev)
+        return S(image_height=cam.height, image_width=cam.width, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=self.bg,
+                 scale_modifier=1.0, viewmatrix=t(cam.viewmatrix), projmatrix=t(cam.projmatrix), sh_degree=self.sh_degree,
+                 campos=t(cam.campos), prefiltered=False, debug=False, include_feature=True,
+                 confidence=torch.ones((self.P, 1), device=self.dev))
+
+    def _xyz_schedule(self):
+        hp = self.hp
+        return (hp["position_lr_init"] * hp["spatial_lr_scale"], hp["position_lr_final"] * hp["spatial_lr_scale"],
+                hp["position_lr_delay_mult"], float(hp["position_lr_max_steps"]))
+
+    def set_hparams(self, step=None, **changes):
+        """(Re)write the device-side hyper-parameter block; `step` is the Adam step count of the NEXT update."""
+        self.hp.update(changes)
+        hp = self.hp
+        if step is None:
+            step = self.iteration + 1
+        li, lf, dm, ms = self._xyz_schedule()
+        xyz_lr = expon_lr(step, li, lf, lr_delay_mult=dm, max_steps=ms)
+        vals = [float(step), xyz_lr, hp["feature_lr"], hp["feature_lr"] / 20.0, hp["opacity_lr"], hp["scaling_lr"], hp["rotation_lr"],
+                hp["language_feature_lr"], hp["beta1"], hp["beta2"], hp["eps"], hp["lambda_dssim"], hp["depth_weight"], 0.0, 0.0, 0.0]
+        self.hp_dev.copy_(torch.tensor(vals, dtype=torch.float32))  # synchronous: not on the per-step path
+
+    def _param_state(self, view):
+        ps = ParamState()
+        ps.P = self.P
+        seg = dict(xyz="xyz", shs="shs", opacity="opacity", scaling="scaling", rotation="rotation", feature="language_feature")
+        for k in self.widths:
+            setattr(ps, k, self.raw[k].data_ptr())
+            setattr(ps, "m_" + k, self.m[k].data_ptr())
+            setattr(ps, "v_" + k, self.v[k].data_ptr())
+            setattr(ps, "g_" + k, self.bucket.segment(seg[k]).data_ptr())
+        ps.opacity_act, ps.scaling_act, ps.rotation_act = (self.act["opacity"].data_ptr(), self.act["scaling"].data_ptr(),
+                                                           self.act["rotation"].data_ptr())
+        if view is not None:
+            ps.g_means2D = self.g_means2D.data_ptr()
+            ps.radii = self.sessions[view].radii.data_ptr()
+            ps.xyz_gradient_accum = self.bucket.segment("xyz_gradient_accum").data_ptr()
+            ps.denom = self.bucket.segment("denom").data_ptr()
+            ps.max_radii2D = self.bucket.max_radii2D.data_ptr()
+        return ps
+
+    def _refresh_activations(self):
+        ps = self._param_state(None)
+        check(lib.b200gs_param_step(C.byref(ps), self.hp_dev.data_ptr(), 0, rz._stream()))
+
+    def _front(self, view):
+        """render, losses (+ cotangents), rasterizer backward."""
+        s = self.sessions[view]
+        s.forward()
+        st = rz._stream()
+        check(lib.b200gs_photometric_loss(s.color.data_ptr(), self.gt[view].data_ptr(), self.W, self.H, self.hp_dev.data_ptr(),
+                                          self.scratch.data_ptr(), self.accum.data_ptr(), self.loss.data_ptr(),
+                                          s.cot["color"].data_ptr(), st))
+        check(lib.b200gs_depth_pearson_loss(s.depth.data_ptr(), self.mono[view].data_ptr(), self.W * self.H, self.hp_dev.data_ptr(),
+                                            self.accum[4:].data_ptr(), self.loss.data_ptr(), s.cot["depth"].data_ptr(), st))
+        s.backward()
+
+    def _back(self, view):
+        ps = self._param_state(view)
+        check(lib.b200gs_param_step(C.byref(ps), self.hp_dev.data_ptr(), 1, rz._stream()))
+        li, lf, dm, ms = self._xyz_schedule()
+        check(lib.b200gs_hparams_advance(self.hp_dev.data_ptr(), li, lf, dm, ms, rz._stream()))
+
+    # ------------------------------------------------------------------ public
+    def step_eager(self, view):
+        """One iteration without graphs (same kernels)."""
+        self.iteration += 1
+        self._front(view)
+        if parallel.world()[1] > 1:
+            self.bucket.all_reduce()
+        self._back(view)
+
+    def capture(self):
+        """Capture one CUDA graph per view (front [+ back when single-GPU])."""
+        world = parallel.world()[1]
+        self.graphs = []
+        side = torch.cuda.Stream(device=self.dev)
+        for v in range(len(self.sessions)):
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(side):  # warm-up outside capture (lazy module loading must not happen while capturing)
+                self._front(v)
+            torch.cuda.current_stream(self.dev).wait_stream(side)
+            torch.cuda.synchronize(self.dev)
+            ga = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga):
+                self._front(v)
+                if world == 1:
+                    self._back(v)
+            gb = None
+            if world > 1:
+                gb = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gb):
+                    self._back(v)
+            self.graphs.append((ga, gb))
+        # the warm-up / capture passes ran the front part with the initial hparams only: no parameter was changed
+        return self
+
+    def step(self, view):
+        """One training iteration on `view`: replay.  Returns nothing; read `loss_values()` when needed (it synchronizes)."""
+        self.iteration += 1
+        ga, gb = self.graphs[view]
+        ga.replay()
+        if gb is not None:
+            self.bucket.all_reduce()
+            gb.replay()
+
+    def loss_values(self):
+        """(total, L1, SSIM, weighted depth loss) of the last step."""
+        t = self.loss.cpu().numpy()
+        return float(t[0]), float(t[1]), float(t[2]), float(t[3])
+
+    def parameters(self):
+        return {k: v for k, v in self.raw.items()}

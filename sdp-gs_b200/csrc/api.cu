@@ -71,6 +71,8 @@ int check_stage(const b200gs_view_t* v, cudaStream_t s, const char* what) {
 
 }  // namespace
 
+int train_fail(int code, const char* msg) { return fail(code, "%s", msg); }
+
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 unsigned pdl_mask() {

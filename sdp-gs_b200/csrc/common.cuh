@@ -129,7 +129,7 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 unsigned pdl_mask();  // B200GS_PDL=<bitmask of launch sites> (0 turns programmatic launches off; A/B measurements)
-enum PdlSite { PDL_SORT = 1, PDL_EMIT = 2, PDL_RANGES = 4, PDL_BLEND_FWD = 8, PDL_PRE_BWD = 16 };
+enum PdlSite { PDL_SORT = 1, PDL_EMIT = 2, PDL_RANGES = 4, PDL_BLEND_FWD = 8, PDL_PRE_BWD = 16, PDL_TRAIN = 32 };
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_impl(unsigned site, void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args&&... args) {

@@ -1,0 +1,208 @@
+"""Training-step kernels (include/b200gs_train.h) against the plain-PyTorch restatement of the reference's torch
+code (oracle/train_torch.py): loss values and gradients, the fused activation + Adam step, and K whole iterations of
+GaussianTrainer (one CUDA-graph replay each) against rasterizer-through-autograd + torch losses + torch.optim.Adam.
+
+Tolerances (floating point): loss values 1e-5 relative; dL/dimage, dL/ddepth 1e-6 absolute / 1e-4 relative to the
+largest entry; parameters after K Adam steps 2e-4 of the group's learning rate x K for >= 99.9 % of the elements
+(Adam's first steps move every element by ~lr * sign(g): an element whose gradient is numerically zero may flip)."""
+import ctypes as C
+import re
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+
+gpu = pytest.mark.gpu
+
+
+def test_train_header_symbols_are_exported():
+    from b200gs import _lib
+    src = open(os.path.join(helpers.ROOT, "include", "b200gs_train.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = sorted(set(re.findall(r"\b(b200gs_[a-z_0-9]+)\s*\(", src)))
+    assert sorted(_lib.TRAIN_EXPORTS) == names
+    raw = C.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n)
+    assert C.sizeof(_lib.HParams) == 64
+    # no-GPU argument checks
+    assert raw.b200gs_param_step(None, None, 1, None) == -1
+
+
+def _hp_block(dev, **kw):
+    vals = dict(step=1.0, lr_xyz=1.6e-4, lr_f_dc=2.5e-3, lr_f_rest=2.5e-3 / 20, lr_opacity=0.05, lr_scaling=5e-3, lr_rotation=1e-3,
+                lr_feature=0.013, beta1=0.9, beta2=0.999, eps=1e-15, lambda_dssim=0.2, depth_weight=0.05)
+    vals.update(kw)
+    order = ["step", "lr_xyz", "lr_f_dc", "lr_f_rest", "lr_opacity", "lr_scaling", "lr_rotation", "lr_feature", "beta1", "beta2",
+             "eps", "lambda_dssim", "depth_weight"]
+    return torch.tensor([vals[k] for k in order] + [0.0] * 3, dtype=torch.float32, device=dev), vals
+
+
+@gpu
+@pytest.mark.parametrize("W,H", [(125, 93), (504, 378), (16, 16)])
+def test_photometric_and_depth_loss_match_torch(W, H):
+    from b200gs._lib import lib, check
+    from oracle import train_torch as tt
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device="cpu").manual_seed(W * 1000 + H)
+    img = torch.rand((3, H, W), generator=g).to(dev)
+    gt = (0.7 * img.cpu() + 0.3 * torch.rand((3, H, W), generator=g)).to(dev)
+    depth = (torch.rand((1, H, W), generator=g) * 5 + 1).to(dev)
+    mono = (0.5 * depth.cpu() + torch.rand((1, H, W), generator=g) * 2 + 0.5).to(dev)
+    hp, vals = _hp_block(dev)
+    accum = torch.zeros(20, dtype=torch.float64, device=dev)
+    loss = torch.zeros(4, dtype=torch.float64, device=dev)
+    scratch = torch.empty(lib.b200gs_photometric_scratch_bytes(W, H) // 4, dtype=torch.float32, device=dev)
+    d_img = torch.full((3, H, W), float("nan"), device=dev)
+    d_depth = torch.full((1, H, W), float("nan"), device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for _ in range(2):  # twice: the accumulators must be left clean
+        check(lib.b200gs_photometric_loss(img.data_ptr(), gt.data_ptr(), W, H, hp.data_ptr(), scratch.data_ptr(), accum.data_ptr(),
+                                          loss.data_ptr(), d_img.data_ptr(), st))
+        check(lib.b200gs_depth_pearson_loss(depth.data_ptr(), mono.data_ptr(), W * H, hp.data_ptr(), accum[4:].data_ptr(),
+                                            loss.data_ptr(), d_depth.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert float(accum[:10].abs().sum()) == 0.0
+
+    ti, td = img.clone().requires_grad_(True), depth.clone().requires_grad_(True)
+    total, l1, s, dl = tt.total_loss(ti, gt, td, mono, vals["lambda_dssim"], vals["depth_weight"])
+    total.backward()
+    got = loss.cpu().numpy()
+    np.testing.assert_allclose(got[0], float(total), rtol=1e-5)
+    np.testing.assert_allclose(got[1], float(l1), rtol=1e-5)
+    np.testing.assert_allclose(got[2], float(s), rtol=1e-5)
+    np.testing.assert_allclose(got[3], float(dl), rtol=1e-5, atol=1e-9)
+    for mine, ref in ((d_img, ti.grad), (d_depth, td.grad)):
+        scale = float(ref.abs().max())
+        assert float((mine - ref).abs().max()) <= 1e-6 + 1e-4 * scale
+
+
+@gpu
+def test_param_step_matches_torch_adam():
+    from b200gs._lib import lib, check, ParamState
+    from oracle import train_torch as tt
+    dev = torch.device("cuda", 0)
+    P = 5003
+    g = torch.Generator(device="cpu").manual_seed(7)
+    shapes = dict(xyz=(P, 3), shs=(P, 48), opacity=(P, 1), scaling=(P, 3), rotation=(P, 4), feature=(P, 3))
+    raw0 = {k: torch.randn(s, generator=g).to(dev) for k, s in shapes.items()}
+    raw0["scaling"] = raw0["scaling"] * 0.3 - 3.0
+    mine = {k: v.clone() for k, v in raw0.items()}
+    m = {k: torch.zeros_like(v) for k, v in mine.items()}
+    v_ = {k: torch.zeros_like(v) for k, v in mine.items()}
+    grads = {k: torch.zeros_like(v) for k, v in mine.items()}
+    act = dict(opacity=torch.empty((P, 1), device=dev), scaling=torch.empty((P, 3), device=dev), rotation=torch.empty((P, 4), device=dev))
+    g2d = torch.zeros((P, 3), device=dev)
+    radii = torch.zeros((P,), dtype=torch.int32, device=dev)
+    accum, denom = torch.zeros((P, 1), device=dev), torch.zeros((P, 1), device=dev)
+    maxr = torch.zeros((P,), dtype=torch.int32, device=dev)
+    ps = ParamState()
+    ps.P = P
+    for k in shapes:
+        setattr(ps, k, mine[k].data_ptr()); setattr(ps, "m_" + k, m[k].data_ptr())
+        setattr(ps, "v_" + k, v_[k].data_ptr()); setattr(ps, "g_" + k, grads[k].data_ptr())
+    ps.opacity_act, ps.scaling_act, ps.rotation_act = act["opacity"].data_ptr(), act["scaling"].data_ptr(), act["rotation"].data_ptr()
+    ps.g_means2D, ps.radii = g2d.data_ptr(), radii.data_ptr()
+    ps.xyz_gradient_accum, ps.denom, ps.max_radii2D = accum.data_ptr(), denom.data_ptr(), maxr.data_ptr()
+
+    tr = dict(xyz=raw0["xyz"].clone(), f_dc=raw0["shs"].view(P, 16, 3)[:, :1].clone(), f_rest=raw0["shs"].view(P, 16, 3)[:, 1:].clone(),
+              opacity=raw0["opacity"].clone(), scaling=raw0["scaling"].clone(), rotation=raw0["rotation"].clone(),
+              feature=raw0["feature"].clone())
+    tr = {k: t.requires_grad_(True) for k, t in tr.items()}
+    hpd = dict(language_feature_lr=0.013, feature_lr=2.5e-3, position_lr_init=1.6e-4, spatial_lr_scale=1.0, opacity_lr=0.05,
+               scaling_lr=5e-3, rotation_lr=1e-3)
+    opt = tt.make_optimizer(tr, hpd)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    t_accum, t_denom, t_maxr = torch.zeros((P, 1), device=dev), torch.zeros((P, 1), device=dev), torch.zeros((P,), dtype=torch.int32, device=dev)
+    for step in range(1, 4):
+        ga = {k: torch.randn(s, generator=g).to(dev) * 1e-3 for k, s in shapes.items()}
+        ga["xyz"][::7] = 0.0  # rows that received no gradient at all
+        g2d.copy_(torch.randn((P, 3), generator=g).to(dev))
+        radii.copy_((torch.rand((P,), generator=g) * 30 - 5).to(torch.int32).to(dev))
+        for k in shapes:
+            grads[k].copy_(ga[k])
+        hp, _ = _hp_block(dev, step=float(step))
+        check(lib.b200gs_param_step(C.byref(ps), hp.data_ptr(), 1, st))
+        a = tt.activate(tr)
+        (a["xyz"] * ga["xyz"]).sum().add_((a["shs"].reshape(P, 48) * ga["shs"]).sum()).add_((a["opacity"] * ga["opacity"]).sum()) \
+            .add_((a["scaling"] * ga["scaling"]).sum()).add_((a["rotation"] * ga["rotation"]).sum()) \
+            .add_((a["feature"] * ga["feature"]).sum()).backward()
+        opt.step(); opt.zero_grad(set_to_none=True)
+        vis = radii > 0
+        t_accum[vis] += torch.norm(g2d[vis, :2], dim=-1, keepdim=True)
+        t_denom[vis] += 1
+        t_maxr[vis] = torch.max(t_maxr[vis], radii[vis])
+    torch.cuda.synchronize()
+    ref = dict(xyz=tr["xyz"], shs=torch.cat((tr["f_dc"], tr["f_rest"]), 1).reshape(P, 48), opacity=tr["opacity"], scaling=tr["scaling"],
+               rotation=tr["rotation"], feature=tr["feature"])
+    lrs = dict(xyz=1.6e-4, shs=2.5e-3, opacity=0.05, scaling=5e-3, rotation=1e-3, feature=0.013)
+    for k in shapes:
+        err = (mine[k] - ref[k].detach()).abs()
+        assert float((err <= 2e-4 * lrs[k] * 3 + 1e-7).float().mean()) >= 0.999, k
+    a = tt.activate(tr)
+    assert float((act["opacity"] - a["opacity"]).abs().max()) < 1e-5
+    assert float((act["scaling"] - a["scaling"]).abs().max()) < 1e-5
+    assert float((act["rotation"] - a["rotation"]).abs().max()) < 1e-5
+    assert torch.allclose(accum, t_accum, rtol=1e-6, atol=1e-7) and torch.equal(denom, t_denom) and torch.equal(maxr, t_maxr)
+
+
+def _trainer_inputs(name, dev):
+    from b200gs import synthetic as syn
+    sc = syn.make_config(name)
+    rng = np.random.default_rng(5)
+    cams = sc.cameras
+    H, W = cams[0].height, cams[0].width
+    gts = [rng.uniform(0, 1, size=(3, H, W)).astype(np.float32) for _ in cams]
+    monos = [rng.uniform(1, 8, size=(1, H, W)).astype(np.float32) for _ in cams]
+    raw = dict(xyz=sc.means3D, shs=sc.shs, opacity_raw=np.log(sc.opacities / (1 - sc.opacities)), scaling_raw=np.log(sc.scales),
+               rotation_raw=sc.rotations * rng.uniform(0.5, 2.0, size=(sc.P, 1)).astype(np.float32), feature=sc.features)
+    return sc, cams, gts, monos, raw
+
+
+@gpu
+def test_trainer_iterations_match_autograd_pipeline():
+    from b200gs.trainer import GaussianTrainer, expon_lr, DEFAULTS
+    from diff_gaussian_rasterization import GaussianRasterizer
+    from oracle import train_torch as tt
+    dev = torch.device("cuda", 0)
+    sc, cams, gts, monos, raw = _trainer_inputs("small", dev)
+    P = sc.P
+    tr = GaussianTrainer(cameras=cams, gt_images=gts, depth_mono=monos, device=dev, capacity=400_000, **raw)
+    tr.capture()
+    # the reference pipeline: activations + losses + Adam in torch, the same rasterizer through autograd
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+    leaf = dict(xyz=t(raw["xyz"]), f_dc=t(raw["shs"][:, :1]), f_rest=t(raw["shs"][:, 1:]), opacity=t(raw["opacity_raw"]).reshape(P, 1),
+                scaling=t(raw["scaling_raw"]), rotation=t(raw["rotation_raw"]), feature=t(raw["feature"]))
+    leaf = {k: v.requires_grad_(True) for k, v in leaf.items()}
+    hp = dict(DEFAULTS)
+    opt = tt.make_optimizer(leaf, hp)
+    K = 4
+    for it in range(1, K + 1):
+        view = (it - 1) % len(cams)
+        tr.step(view)
+        mine = tr.loss_values()
+        tt.set_xyz_lr(opt, expon_lr(it, hp["position_lr_init"], hp["position_lr_final"], lr_delay_mult=hp["position_lr_delay_mult"],
+                                    max_steps=hp["position_lr_max_steps"]))
+        a = tt.activate(leaf)
+        means2D = torch.zeros((P, 3), device=dev, requires_grad=True)
+        color, depth, alpha, feat, radii = GaussianRasterizer(tr._default_settings(cams[view]))(
+            means3D=a["xyz"], means2D=means2D, opacities=a["opacity"], shs=a["shs"], scales=a["scaling"], rotations=a["rotation"],
+            shs_language=a["feature"])
+        total, l1, s, dl = tt.total_loss(color, t(gts[view]), depth, t(monos[view]), hp["lambda_dssim"], hp["depth_weight"])
+        total.backward()
+        opt.step(); opt.zero_grad(set_to_none=True)
+        np.testing.assert_allclose(mine, [float(total), float(l1), float(s), float(dl)], rtol=2e-4, atol=1e-7)
+    torch.cuda.synchronize()
+    ref = dict(xyz=leaf["xyz"], shs=torch.cat((leaf["f_dc"], leaf["f_rest"]), 1).reshape(P, 48), opacity=leaf["opacity"],
+               scaling=leaf["scaling"], rotation=leaf["rotation"], feature=leaf["feature"])
+    lrs = dict(xyz=hp["position_lr_init"], shs=hp["feature_lr"], opacity=hp["opacity_lr"], scaling=hp["scaling_lr"],
+               rotation=hp["rotation_lr"], feature=hp["language_feature_lr"])
+    for k, p in tr.parameters().items():
+        err = (p - ref[k].detach()).abs()
+        frac = float((err <= 0.05 * lrs[k] * K + 1e-7).float().mean())
+        assert frac >= 0.99, (k, frac, float(err.max()))
+    # densification statistics were maintained
+    assert float(tr.bucket.segment("denom").sum()) > 0
