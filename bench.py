@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--P", type=int, default=None, help="override the Gaussian count of the workload")
     ap.add_argument("--fwd-only", action="store_true", help="forward only (render throughput, BASELINE configs[3])")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-iteration measurement (`train` key)")
     return ap.parse_args()
 
 
@@ -374,6 +375,10 @@ def run_b200gs(args, rank, world, local):
                     stage_ms=stage_ms, stage_sum_ms=sum(stage_ms.values()),
                     note="blend stages are FP32/SFU bound (256*L pair evaluations), not HBM bound; see DESIGN.md")
 
+    train = None
+    if not args.fwd_only and ext and not args.no_train:
+        train = train_b200gs(args, wl, capacity, rank, world, flush)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(wl, 0)
@@ -394,9 +399,104 @@ def run_b200gs(args, rank, world, local):
                                   "every step's parameters are uploaded from pinned host memory (b200gs.hostio.PinnedFeeder: one copy per "
                                   "step on a copy stream, step i+1's upload overlapping step i's kernels); color.sum().item() read back"),
                     gpu_launches=int(launches_per_step * args.steps), gpu_launches_per_step=int(launches_per_step),
-                    clocks=clocks, roofline=roofline, cpu_baseline=cpu, vanilla=vanilla, impl="b200gs",
+                    clocks=clocks, roofline=roofline, cpu_baseline=cpu, vanilla=vanilla, train=train, impl="b200gs",
                     wall_s=wall)
         print(json.dumps(line))
+
+
+def train_targets(wl):
+    """Synthetic supervision of the training-iteration measurement: fixed-seed ground-truth images and monocular depth
+    maps of the workload's shape (their content does not change the work done)."""
+    rng = np.random.default_rng(4242)
+    gts = [rng.uniform(0, 1, size=(3, wl.H, wl.W)).astype(np.float32) for _ in wl.cams]
+    monos = [rng.uniform(1, 8, size=(1, wl.H, wl.W)).astype(np.float32) for _ in wl.cams]
+    return gts, monos
+
+
+def raw_params(sc):
+    """Pre-activation parameters of the synthetic scene (inverse of scene/gaussian_model.py:44-57)."""
+    op = np.clip(sc.opacities, 1e-6, 1 - 1e-6)
+    return dict(xyz=sc.means3D, shs=sc.shs, opacity_raw=np.log(op / (1 - op)), scaling_raw=np.log(sc.scales),
+                rotation_raw=sc.rotations, feature=sc.features)
+
+
+TRAIN_WHAT = ("one training iteration = render (color+depth+alpha+feature) + L1/SSIM + Pearson-depth losses + rasterizer backward + "
+              "activations/Adam over the 7 parameter groups + densification statistics; one view per iteration")
+
+
+def train_b200gs(args, wl, capacity, rank, world, flush):
+    from b200gs.trainer import GaussianTrainer
+    gts, monos = train_targets(wl)
+    tr = GaussianTrainer(cameras=wl.cams, gt_images=gts, depth_mono=monos, device=wl.dev, capacity=capacity, **raw_params(wl.scene))
+    tr.capture()
+    nviews = len(wl.cams)
+    ms, _ = event_loop(args.steps, args.warmup, lambda i: tr.step((i + rank) % nviews), flush, world)
+    loss = tr.loss_values()
+    for s in tr.sessions:
+        n, ov = s.status()
+        assert ov == 0, "binning capacity overflow in the training loop"
+    ms_it = ms / args.steps
+    return dict(iters_per_s=world * 1000.0 / ms_it, ms_per_iter=ms_it, what=TRAIN_WHAT + ", whole iteration = one CUDA-graph replay"
+                + (" + one NCCL all-reduce" if world > 1 else ""), last_loss=loss[0])
+
+
+def train_reference(args, wl, binning_bytes, flush):
+    """The reference's stock path for the same iteration: its CUDA rasterizer through autograd (color via SH; depth via a
+    second call with colors_precomp = (z, 1, f0), bg 0 -- the vendored kernel has no depth output), torch activations,
+    torch losses (utils/loss_utils.py restated in oracle/train_torch.py) and torch.optim.Adam with its 7 groups."""
+    from oracle import ref_cuda, train_torch as tt
+    from b200gs.trainer import DEFAULTS, expon_lr
+    dev = wl.dev
+    P = wl.scene.P
+    gts, monos = train_targets(wl)
+    gts, monos = [torch.from_numpy(g).to(dev) for g in gts], [torch.from_numpy(m).to(dev) for m in monos]
+    rp = raw_params(wl.scene)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+    leaf = dict(xyz=t(rp["xyz"]), f_dc=t(rp["shs"][:, :1]), f_rest=t(rp["shs"][:, 1:]), opacity=t(rp["opacity_raw"]).reshape(P, 1),
+                scaling=t(rp["scaling_raw"]), rotation=t(rp["rotation_raw"]), feature=t(rp["feature"]))
+    leaf = {k: v.requires_grad_(True) for k, v in leaf.items()}
+    hp = dict(DEFAULTS)
+    opt = tt.make_optimizer(leaf, hp)
+    cfgs = []
+    zero3 = torch.zeros(3, device=dev)
+    for cam in wl.cams:
+        base = dict(cam=cam, view=t(cam.viewmatrix), proj=t(cam.projmatrix), campos=t(cam.campos), binning_bytes=binning_bytes)
+        cfgs.append((dict(base, bg=wl.bg, D=3), dict(base, bg=zero3, D=0)))
+    nviews = len(wl.cams)
+    state = dict(it=0, loss=0.0)
+
+    def step(i):
+        state["it"] += 1
+        vi = i % nviews
+        c_rgb, c_pack = cfgs[vi]
+        tt.set_xyz_lr(opt, expon_lr(state["it"], hp["position_lr_init"], hp["position_lr_final"], lr_delay_mult=hp["position_lr_delay_mult"],
+                                    max_steps=hp["position_lr_max_steps"]))
+        a = tt.activate(leaf)
+        means2D = torch.zeros((P, 3), device=dev, requires_grad=True)
+        color, radii = ref_cuda.RefRasterize.apply(a["xyz"], means2D, a["shs"], None, a["opacity"], a["scaling"], a["rotation"], c_rgb)
+        z = a["xyz"] @ c_rgb["view"][:3, 2] + c_rgb["view"][3, 2]
+        f = a["feature"] * 0.28209479177387814
+        f = f / (f.norm(dim=-1, keepdim=True) + 1e-9)
+        packed = torch.stack((z, torch.ones_like(z), f[:, 0]), dim=1)
+        pk, _ = ref_cuda.RefRasterize.apply(a["xyz"], means2D, None, packed, a["opacity"], a["scaling"], a["rotation"], c_pack)
+        total, l1, ss, dl = tt.total_loss(color, gts[vi], pk[0:1], monos[vi], hp["lambda_dssim"], hp["depth_weight"])
+        total.backward()
+        with torch.no_grad():  # train.py:218-221
+            vis = radii > 0
+            stats["max_radii2D"][vis] = torch.max(stats["max_radii2D"][vis], radii[vis])
+            stats["accum"][vis] += torch.norm(means2D.grad[vis, :2], dim=-1, keepdim=True)
+            stats["denom"][vis] += 1
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        state["loss"] = total
+
+    stats = dict(max_radii2D=torch.zeros((P,), dtype=torch.int32, device=dev), accum=torch.zeros((P, 1), device=dev),
+                 denom=torch.zeros((P, 1), device=dev))
+    ms, _ = event_loop(args.steps, args.warmup, step, flush, 1)
+    ms_it = ms / args.steps
+    return dict(iters_per_s=1000.0 / ms_it, ms_per_iter=ms_it, last_loss=float(state["loss"]),
+                what=TRAIN_WHAT + "; reference CUDA rasterizer through autograd (2 calls: SH colour; packed z for the depth map), "
+                                  "torch activations / losses / Adam, eager")
 
 
 def cpu_baseline(wl, vi):
@@ -533,6 +633,9 @@ def run_reference(args, rank, world, local):
         return float(rb.color.sum().item())
 
     e2e_sec = wall_loop(args.steps, max(3, args.warmup), step_e2e, 1)
+    train = None
+    if ext and not args.fwd_only and not args.no_train:
+        train = train_reference(args, wl, rb.bb, flush)
     calls = 3 if ext else 1
     print(json.dumps(dict(
         impl="reference", metric="rasterizer fwd+bwd views/s (1000/ms_per_step = ms/view; one view per train iteration)",
@@ -546,7 +649,7 @@ def run_reference(args, rank, world, local):
                          "the reference has no distributed path: it runs on rank 0's GPU only, whatever N is"),
         e2e=dict(value=args.steps / e2e_sec, unit="views/s", ms_per_step=1000.0 * e2e_sec / args.steps,
                  h2d_bytes_per_step=wl.h2d_bytes, d2h_bytes_per_step=4 + 4 * calls),
-        gpu_launches=0, clocks=clocks, vanilla=vanilla,
+        gpu_launches=0, clocks=clocks, vanilla=vanilla, train=train,
         cpu_baseline=dict(value=None, unit="views/s", cores=0, kind="reference",
                           sample="the reference path is CUDA-only: this arm runs its own kernels on the B200, not a CPU port"),
         wall_s=wall)))

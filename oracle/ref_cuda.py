@@ -162,3 +162,63 @@ def mark_visible(means3D, cam):
     L.ref_mark_visible(C.c_int(m.shape[0]), _p(m), _p(v), _p(p), _p(present))
     torch.cuda.synchronize()
     return present.cpu().numpy()
+
+
+class RefRasterize(torch.autograd.Function):
+    """The reference rasterizer as an autograd op, mirroring `_RasterizeGaussians`
+    (DGR/diff_gaussian_rasterization/__init__.py:44-155) with the allocation pattern of its binding
+    (DGR/rasterize_points.cu:60-77 outputs + byte buffers, :151-159 nine zero-filled gradient tensors).
+    Used by bench.py's reference arm to time a training iteration of the reference's stock path.
+    `cfg` = dict(cam, view, proj, campos, bg, D, binning_bytes)."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cfg):
+        L = lib()
+        cam = cfg["cam"]
+        P, W, H = means3D.shape[0], int(cam.width), int(cam.height)
+        M = 0 if sh is None else int(sh.shape[1])
+        color = torch.full((3, H, W), 0.0, dtype=torch.float32, device=means3D.device)
+        radii = torch.full((P,), 0, dtype=torch.int32, device=means3D.device)
+        gb, ib = L.ref_required_geom(P), L.ref_required_image(W * H)
+        geom = torch.empty((gb,), dtype=torch.uint8, device=means3D.device)
+        img = torch.empty((ib,), dtype=torch.uint8, device=means3D.device)
+        binning = torch.empty((cfg["binning_bytes"],), dtype=torch.uint8, device=means3D.device)
+        needed = C.c_size_t(0)
+        means3D, opacities = means3D.contiguous(), opacities.contiguous()
+        sh = None if sh is None else sh.contiguous()
+        colors_precomp = None if colors_precomp is None else colors_precomp.contiguous()
+        scales, rotations = scales.contiguous(), rotations.contiguous()
+        n = L.ref_forward(C.c_int(P), C.c_int(cfg["D"]), C.c_int(M), _p(cfg["bg"]), C.c_int(W), C.c_int(H), _p(means3D), _p(sh),
+                          _p(colors_precomp), _p(opacities), _p(scales), C.c_float(1.0), _p(rotations), None, _p(cfg["view"]),
+                          _p(cfg["proj"]), _p(cfg["campos"]), C.c_float(cam.tanfovx), C.c_float(cam.tanfovy), C.c_int(0), _p(color),
+                          _p(radii), _p(geom), C.c_size_t(gb), _p(binning), C.c_size_t(cfg["binning_bytes"]), C.byref(needed), _p(img),
+                          C.c_size_t(ib), C.c_int(0))
+        if n < 0:
+            raise RuntimeError("reference forward failed: " + L.ref_last_error().decode())
+        ctx.cfg, ctx.n, ctx.M = cfg, int(n), M
+        ctx.has_sh = sh is not None
+        ctx.save_for_backward(means3D, sh if sh is not None else torch.empty(0), colors_precomp if colors_precomp is not None else torch.empty(0),
+                              scales, rotations, radii, geom, binning, img)
+        ctx.mark_non_differentiable(radii)
+        return color, radii
+
+    @staticmethod
+    def backward(ctx, g_color, _g_radii):
+        L = lib()
+        means3D, sh, colors, scales, rotations, radii, geom, binning, img = ctx.saved_tensors
+        cfg, cam = ctx.cfg, ctx.cfg["cam"]
+        P, W, H, M = means3D.shape[0], int(cam.width), int(cam.height), ctx.M
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=means3D.device)
+        g = dict(means2D=z(P, 3), conic=z(P, 2, 2), opacities=z(P, 1), colors=z(P, 3), means3D=z(P, 3), cov3D=z(P, 6),
+                 shs=z(P, max(M, 1), 3), scales=z(P, 3), rotations=z(P, 4))
+        shp = sh if ctx.has_sh else None
+        colp = colors if not ctx.has_sh else None
+        rc = L.ref_backward(C.c_int(P), C.c_int(cfg["D"]), C.c_int(M), C.c_int(ctx.n), _p(cfg["bg"]), C.c_int(W), C.c_int(H), _p(means3D),
+                            _p(shp), _p(colp), _p(scales), C.c_float(1.0), _p(rotations), None, _p(cfg["view"]), _p(cfg["proj"]),
+                            _p(cfg["campos"]), C.c_float(cam.tanfovx), C.c_float(cam.tanfovy), _p(radii), _p(geom), _p(binning), _p(img),
+                            _p(g_color.contiguous()), _p(g["means2D"]), _p(g["conic"]), _p(g["opacities"]), _p(g["colors"]),
+                            _p(g["means3D"]), _p(g["cov3D"]), _p(g["shs"]), _p(g["scales"]), _p(g["rotations"]), C.c_int(0))
+        if rc != 0:
+            raise RuntimeError("reference backward failed")
+        return (g["means3D"], g["means2D"], g["shs"] if ctx.has_sh else None, g["colors"] if not ctx.has_sh else None,
+                g["opacities"], g["scales"], g["rotations"], None)
