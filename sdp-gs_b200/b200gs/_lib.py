@@ -76,6 +76,7 @@ class ParamState(C.Structure):  # b200gs_param_state_t
 
 TRAIN_EXPORTS = ["b200gs_param_step", "b200gs_photometric_loss", "b200gs_photometric_scratch_bytes",
                  "b200gs_depth_pearson_loss", "b200gs_hparams_advance"]
+COLLECTIVE_EXPORTS = ["b200gs_allreduce_sum_f32", "b200gs_allreduce_flag_words"]
 
 EXPORTS = [
     "b200gs_version", "b200gs_last_error", "b200gs_geom_bytes", "b200gs_image_bytes", "b200gs_binning_bytes",
@@ -92,7 +93,7 @@ def _load():
             f"{LIB_PATH} not found: build it with `make -C sdp-gs_b200/csrc` (or __graft_entry__.build()). "
             "b200gs has no CPU / PyTorch fallback.")
     lib = C.CDLL(LIB_PATH)
-    for name in EXPORTS + TRAIN_EXPORTS:
+    for name in EXPORTS + TRAIN_EXPORTS + COLLECTIVE_EXPORTS:
         if not hasattr(lib, name):
             raise ImportError(f"{LIB_PATH} does not export {name}")
     lib.b200gs_last_error.restype = C.c_char_p
@@ -125,6 +126,9 @@ def _load():
     lib.b200gs_depth_pearson_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                               C.c_void_p]
     lib.b200gs_hparams_advance.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    lib.b200gs_allreduce_flag_words.argtypes = [C.c_int32]
+    lib.b200gs_allreduce_flag_words.restype = C.c_size_t
+    lib.b200gs_allreduce_sum_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
     assert C.sizeof(HParams) == 64
     sizes = (C.c_int64 * 6)()
     lib.b200gs_abi_sizes(sizes)

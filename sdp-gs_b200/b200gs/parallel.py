@@ -14,6 +14,8 @@ same code runs under gloo on CPU for the host-logic tests).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -35,16 +37,71 @@ def world():
     return 0, 1
 
 
+class _SymmetricBuffer:
+    """A float32 buffer allocated at the same offset of a peer-mapped allocation on every rank
+    (torch.distributed._symmetric_memory supplies the allocation, the handle exchange and the NVLS multicast mapping;
+    the reduction itself is b200gs_allreduce_sum_f32)."""
+
+    @classmethod
+    def create(cls, n_floats, device, mode):
+        try:
+            import torch.distributed._symmetric_memory as symm
+            from ._lib import lib
+            self = cls()
+            rank, n = world()
+            self.rank, self.world = rank, n
+            self.tensor = symm.empty(n_floats, dtype=torch.float32, device=device)
+            self.tensor.zero_()
+            self.hdl = symm.rendezvous(self.tensor, dist.group.WORLD)
+            words = int(lib.b200gs_allreduce_flag_words(n))
+            self.flags = symm.empty(words, dtype=torch.int32, device=device)
+            self.flags.zero_()
+            self.fhdl = symm.rendezvous(self.flags, dist.group.WORLD)
+            mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+            # NVLS multimem measured slower than plain P2P at 2 GPUs (85 vs 58 us for 24.8 MB): opt-in only
+            self.multicast = mc if mode == "multimem" else 0
+            if mode == "multimem" and not mc:
+                raise RuntimeError("no NVLS multicast mapping for the symmetric buffer")
+            torch.cuda.synchronize(device)
+            dist.barrier()
+            return self
+        except Exception as ex:  # not fatal: NCCL does the same sum
+            if os.environ.get("B200GS_ALLREDUCE", "auto") in ("p2p", "multimem"):
+                raise
+            import warnings
+            warnings.warn(f"symmetric gradient buffer unavailable ({type(ex).__name__}: {ex}); using NCCL all-reduce")
+            return None
+
+    def all_reduce(self, offset_floats, n_floats):
+        import ctypes as C
+        from ._lib import check, lib
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        check(lib.b200gs_allreduce_sum_f32(C.c_void_p(int(self.hdl.buffer_ptrs_dev)), C.c_void_p(int(self.fhdl.buffer_ptrs_dev)),
+                                           C.c_void_p(self.multicast) if self.multicast else None, C.c_int64(offset_floats),
+                                           C.c_int64(n_floats), self.rank, self.world, stream))
+
+
 class FusedGradBuffer:
     """One flat f32 allocation of P*64 floats holding every per-Gaussian quantity of an image-parallel
     step as back-to-back contiguous segments ([P,3] xyz, [P,16,3] shs = f_dc + f_rest, [P,1] opacity, ...).
     The rasterizer backward can write straight into the segments (they are ordinary contiguous tensors), so
     combining all ranks' gradients is ONE all-reduce with no packing pass."""
 
-    def __init__(self, P, device, sh_coeffs=16):
+    def __init__(self, P, device, sh_coeffs=16, symmetric=None):
         assert sh_coeffs == 16, "segment table assumes max_sh_degree = 3 (arguments/__init__.py:49)"
         self.P = P
-        self.flat = torch.zeros((P * FUSED_WIDTH,), dtype=torch.float32, device=device)
+        self.flat = None
+        self._symm = None
+        rank, n = world()
+        mode = os.environ.get("B200GS_ALLREDUCE", "auto")
+        if symmetric is None:
+            symmetric = n > 1 and torch.device(device).type == "cuda" and mode != "nccl" and (62 * P) % 4 == 0
+        if symmetric:
+            self._symm = _SymmetricBuffer.create(P * FUSED_WIDTH, device, mode)
+            if self._symm is not None:
+                self.flat = self._symm.tensor
+        if self.flat is None:
+            self.flat = torch.zeros((P * FUSED_WIDTH,), dtype=torch.float32, device=device)
         self.max_radii2D = torch.zeros((P,), dtype=torch.int32, device=device)
         self.seg = {}
         c = 0
@@ -95,6 +152,12 @@ class FusedGradBuffer:
         pass with_statistics=True then, or call all_reduce_statistics()."""
         rank, n = world()
         if n == 1:
+            return None
+        if self._symm is not None and not async_op:
+            # our own kernel over NVLink peer memory (include/b200gs_collective.h), on the current stream
+            self._symm.all_reduce(0, (64 if with_statistics else 62) * self.P)
+            if with_statistics:
+                dist.all_reduce(self.max_radii2D, op=dist.ReduceOp.MAX)
             return None
         works = [dist.all_reduce(self.flat if with_statistics else self.grads_flat, op=dist.ReduceOp.SUM, async_op=True)]
         if with_statistics:

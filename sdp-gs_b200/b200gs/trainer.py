@@ -189,13 +189,16 @@ class GaussianTrainer:
                 self._front(v)
             torch.cuda.current_stream(self.dev).wait_stream(side)
             torch.cuda.synchronize(self.dev)
+            own_collective = world > 1 and self.bucket._symm is not None  # our all-reduce kernel can live inside the graph
             ga = torch.cuda.CUDAGraph()
             with torch.cuda.graph(ga):
                 self._front(v)
-                if world == 1:
+                if own_collective:
+                    self.bucket.all_reduce()
+                if world == 1 or own_collective:
                     self._back(v)
             gb = None
-            if world > 1:
+            if world > 1 and not own_collective:
                 gb = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gb):
                     self._back(v)

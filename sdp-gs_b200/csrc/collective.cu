@@ -1,0 +1,142 @@
+// b200gs -- two-shot SUM all-reduce over NVLink peer memory (include/b200gs_collective.h).
+//
+// Algorithmic bytes per rank: reads world * n/world * 4 (own slice from every rank) + writes world * n/world * 4
+// = 8n bytes over NVLink/NVSwitch for n floats, against 2 * (world-1)/world * 4n for a ring: the same wire traffic,
+// but one kernel, two block-level barriers and no intermediate buffers.  With an NVLS multicast mapping the switch
+// performs the reduction (multimem.ld_reduce) and the broadcast (multimem.st): 4n/world read + 4n/world written per rank.
+#include <cstdlib>
+#include "common.cuh"
+#include "../../include/b200gs_collective.h"
+
+int train_fail(int code, const char* msg);  // api.cu
+
+namespace {
+
+constexpr int AR_BLOCKS = 256;   // maximum grid (sizes the flag array); the launch uses ar_blocks()
+// float4 per thread and step = 16 / world: ~16 NVLink requests per thread in flight cover the remote-load latency
+constexpr int AR_THREADS = 512;
+constexpr int AR_MAX_WORLD = 8;
+
+__device__ __forceinline__ void flag_put(uint32_t* addr) {
+	while (atomicCAS_system(addr, 0u, 1u) != 0u) {}
+}
+__device__ __forceinline__ void flag_wait(uint32_t* addr) {
+	while (atomicCAS_system(addr, 1u, 0u) != 1u) {}
+}
+
+// Block b of every rank meets block b of every other rank.  Slot layout of a rank's flag array: [phase][block][source rank].
+__device__ __forceinline__ void block_barrier(void* const* flags, int rank, int world, int phase) {
+	__syncthreads();
+	if ((int)threadIdx.x < world) {
+		const int peer = threadIdx.x;
+		__threadfence_system();
+		uint32_t* theirs = reinterpret_cast<uint32_t*>(flags[peer]) + ((size_t)phase * gridDim.x + blockIdx.x) * AR_MAX_WORLD + rank;
+		uint32_t* mine = reinterpret_cast<uint32_t*>(flags[rank]) + ((size_t)phase * gridDim.x + blockIdx.x) * AR_MAX_WORLD + peer;
+		flag_put(theirs);
+		flag_wait(mine);
+		__threadfence_system();
+	}
+	__syncthreads();
+}
+
+template <int WORLD>
+__global__ void __launch_bounds__(AR_THREADS) allreduce_p2p_kernel(void* const* __restrict__ bufs, void* const* __restrict__ flags,
+                                                                    int64_t off4, int64_t n4, int rank)
+{
+	__shared__ void* s_flags[AR_MAX_WORLD];
+	float4* p[WORLD];
+#pragma unroll
+	for (int r = 0; r < WORLD; r++) p[r] = reinterpret_cast<float4*>(bufs[r]) + off4;
+	if ((int)threadIdx.x < WORLD) s_flags[threadIdx.x] = flags[threadIdx.x];
+	__syncthreads();
+	block_barrier(s_flags, rank, WORLD, 0);  // every rank's producer kernels have finished (stream order) before its flags go up
+	const int64_t per = (n4 + WORLD - 1) / WORLD;
+	const int64_t lo = per * rank, hi = min(n4, lo + per);
+	constexpr int AR_UNROLL = WORLD <= 2 ? 8 : (WORLD <= 4 ? 4 : 2);
+	const int64_t stride = (int64_t)gridDim.x * AR_THREADS;
+	for (int64_t i0 = lo + (int64_t)blockIdx.x * AR_THREADS + threadIdx.x; i0 < hi; i0 += stride * AR_UNROLL) {
+		float4 v[AR_UNROLL][WORLD];
+#pragma unroll
+		for (int u = 0; u < AR_UNROLL; u++) {
+			const int64_t i = i0 + u * stride;
+#pragma unroll
+			for (int r = 0; r < WORLD; r++) v[u][r] = i < hi ? __ldcg(p[r] + i) : make_float4(0.f, 0.f, 0.f, 0.f);  // all loads in flight first
+		}
+#pragma unroll
+		for (int u = 0; u < AR_UNROLL; u++) {
+			const int64_t i = i0 + u * stride;
+			float4 a = v[u][0];  // fixed-order sum: identical on every rank
+#pragma unroll
+			for (int r = 1; r < WORLD; r++) { a.x += v[u][r].x; a.y += v[u][r].y; a.z += v[u][r].z; a.w += v[u][r].w; }
+			if (i < hi) {
+#pragma unroll
+				for (int r = 0; r < WORLD; r++) __stcg(p[r] + i, a);
+			}
+		}
+	}
+	block_barrier(s_flags, rank, WORLD, 1);  // every slice has landed everywhere
+}
+
+__global__ void __launch_bounds__(AR_THREADS) allreduce_multimem_kernel(void* const* __restrict__ flags, float4* mc, int64_t off4, int64_t n4,
+                                                                         int rank, int world)
+{
+	__shared__ void* s_flags[AR_MAX_WORLD];
+	if ((int)threadIdx.x < world) s_flags[threadIdx.x] = flags[threadIdx.x];
+	__syncthreads();
+	block_barrier(s_flags, rank, world, 0);
+	const int64_t per = (n4 + world - 1) / world;
+	const int64_t lo = per * rank, hi = min(n4, lo + per);
+	for (int64_t i = lo + (int64_t)blockIdx.x * AR_THREADS + threadIdx.x; i < hi; i += (int64_t)gridDim.x * AR_THREADS) {
+		float4 a;
+		float4* addr = mc + off4 + i;
+		asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+		             : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(addr) : "memory");
+		asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+	}
+	block_barrier(s_flags, rank, world, 1);
+}
+
+int ar_blocks() {
+	static int v = -1;
+	if (v < 0) {
+		const char* e = getenv("B200GS_AR_BLOCKS");
+		v = e ? atoi(e) : 64;  // measured flat between 16 and 128 blocks (the wire is the bound), slower at 256
+		if (v < 1 || v > AR_BLOCKS) v = 64;
+	}
+	return v;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t b200gs_allreduce_flag_words(int32_t world) { (void)world; return (size_t)2 * AR_BLOCKS * AR_MAX_WORLD; }
+
+int b200gs_allreduce_sum_f32(void* const* buffers_dev, void* const* flags_dev, void* multicast_ptr, int64_t offset_floats,
+                             int64_t n_floats, int32_t rank, int32_t world, void* stream_) {
+	if (!buffers_dev || !flags_dev || world < 1 || world > AR_MAX_WORLD || rank < 0 || rank >= world || n_floats < 0 ||
+	    (n_floats & 3) || (offset_floats & 3))
+		return train_fail(B200GS_E_ARG, "allreduce_sum_f32: bad arguments (world <= 8, offset and n multiples of 4)");
+	if (world == 1 || n_floats == 0) return 0;
+	cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+	const int64_t n4 = n_floats / 4, off4 = offset_floats / 4;
+	if (multicast_ptr) {
+		allreduce_multimem_kernel<<<ar_blocks(), AR_THREADS, 0, stream>>>(flags_dev, reinterpret_cast<float4*>(multicast_ptr), off4, n4, rank, world);
+	} else {
+		switch (world) {
+		case 2: allreduce_p2p_kernel<2><<<ar_blocks(), AR_THREADS, 0, stream>>>(buffers_dev, flags_dev, off4, n4, rank); break;
+		case 3: allreduce_p2p_kernel<3><<<ar_blocks(), AR_THREADS, 0, stream>>>(buffers_dev, flags_dev, off4, n4, rank); break;
+		case 4: allreduce_p2p_kernel<4><<<ar_blocks(), AR_THREADS, 0, stream>>>(buffers_dev, flags_dev, off4, n4, rank); break;
+		case 5: allreduce_p2p_kernel<5><<<ar_blocks(), AR_THREADS, 0, stream>>>(buffers_dev, flags_dev, off4, n4, rank); break;
+		case 6: allreduce_p2p_kernel<6><<<ar_blocks(), AR_THREADS, 0, stream>>>(buffers_dev, flags_dev, off4, n4, rank); break;
+		case 7: allreduce_p2p_kernel<7><<<ar_blocks(), AR_THREADS, 0, stream>>>(buffers_dev, flags_dev, off4, n4, rank); break;
+		default: allreduce_p2p_kernel<8><<<ar_blocks(), AR_THREADS, 0, stream>>>(buffers_dev, flags_dev, off4, n4, rank); break;
+		}
+	}
+	count_launch();
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return train_fail(B200GS_E_CUDA, cudaGetErrorString(e));
+	return 0;
+}
+
+}  // extern "C"
