@@ -218,6 +218,7 @@ def run_b200gs(args, rank, world, local):
     nviews = len(wl.cams)
     flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
     flush = lambda: flush_buf.zero_()
+    own_ar = False
 
     # instance counts per view (one synchronous forward each) -> capacity of the no-sync path
     Ls, Vs = [], []
@@ -244,26 +245,32 @@ def run_b200gs(args, rank, world, local):
             s.cot["color"].copy_(wl.cot[vi][0])
             if ext:
                 s.cot["depth"].copy_(wl.cot[vi][1]); s.cot["alpha"].copy_(wl.cot[vi][2]); s.cot["feature"].copy_(wl.cot[vi][3])
-        s.capture()
+        # our own all-reduce kernel (NVLink peer memory) is part of the captured step; an NCCL fallback stays outside the graph
+        own_ar = world > 1 and not args.fwd_only and bucket._symm is not None
+        if own_ar:
+            s.capture(fn=lambda s=s: (s.step(), bucket.all_reduce()))
+        else:
+            s.capture()
         sessions.append(s)
 
     def step_resident(i):
         sessions[(i + rank) % nviews].replay()
-        if world > 1 and not args.fwd_only:
+        if world > 1 and not args.fwd_only and not own_ar:
             bucket.all_reduce()
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         t_s = time.perf_counter()
+        solo = (lambda: sessions[0].step()) if own_ar else (lambda: sessions[0].replay())  # never a collective: only rank 0 runs these loops
         while time.perf_counter() - t_s < 1.5:  # nvidia-smi needs ~1 s to start: keep the same kernels running meanwhile
-            flush(); sessions[0].replay()       # (no collective here: only rank 0 runs this loop)
+            flush(); solo()
         torch.cuda.synchronize()
     ms_total, wall = event_loop(args.steps, args.warmup, step_resident, flush, world)
     if rank == 0:
         t_s = time.perf_counter()
         while time.perf_counter() - t_s < 0.7:  # a few more samples under the identical load
-            flush(); sessions[0].replay()
+            flush(); solo()
         torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else {}
     for s in sessions:
@@ -389,7 +396,7 @@ def run_b200gs(args, rank, world, local):
                     higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                     config=dict(workload=f"{args.workload}: P={P} Gaussians, {wl.W}x{wl.H}, SH degree 3 in-kernel, "
                                          f"outputs={'color+depth+alpha+feature' if ext else 'color'}, one view {'forward' if args.fwd_only else 'fwd+bwd'} per step"
-                                         + (", per-Gaussian gradient NCCL all-reduce (image-parallel)" if world > 1 else ""),
+                                         + ((", per-Gaussian gradient all-reduce (image-parallel; " + ("own NVLink peer-memory kernel inside the graph" if own_ar else "NCCL") + ")") if world > 1 else ""),
                                 P=P, width=wl.W, height=wl.H, mode=args.mode, num_rendered=L, visible=V, tiles=model["tiles"],
                                 sort_passes_model=model["passes"], l2="flushed between steps (256 MiB write)",
                                 binning="capacity mode, CUDA graph replay", parallelism=f"image-parallel x{world}"),
