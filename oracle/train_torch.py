@@ -91,3 +91,44 @@ def set_xyz_lr(optimizer, lr):
     for g in optimizer.param_groups:
         if g["name"] == "xyz":
             g["lr"] = lr
+
+
+# ---- utils/sh_utils.py:24-112 (constants and eval_sh, degrees 0-3) and the python-SH branch of the render glue
+SH_C0 = 0.28209479177387814
+SH_C1 = 0.4886025119029199
+SH_C2 = [1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396]
+SH_C3 = [-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154, -0.4570457994644658,
+         1.445305721320277, -0.5900435899266435]
+
+
+def eval_sh(deg, sh, dirs):
+    """sh [..., C, (deg+1)^2], dirs [..., 3] unit vectors -> [..., C]"""
+    result = SH_C0 * sh[..., 0]
+    if deg > 0:
+        x, y, z = dirs[..., 0:1], dirs[..., 1:2], dirs[..., 2:3]
+        result = result - SH_C1 * y * sh[..., 1] + SH_C1 * z * sh[..., 2] - SH_C1 * x * sh[..., 3]
+        if deg > 1:
+            xx, yy, zz = x * x, y * y, z * z
+            xy, yz, xz = x * y, y * z, x * z
+            result = (result + SH_C2[0] * xy * sh[..., 4] + SH_C2[1] * yz * sh[..., 5] + SH_C2[2] * (2.0 * zz - xx - yy) * sh[..., 6]
+                      + SH_C2[3] * xz * sh[..., 7] + SH_C2[4] * (xx - yy) * sh[..., 8])
+            if deg > 2:
+                result = (result + SH_C3[0] * y * (3 * xx - yy) * sh[..., 9] + SH_C3[1] * xy * z * sh[..., 10]
+                          + SH_C3[2] * y * (4 * zz - xx - yy) * sh[..., 11] + SH_C3[3] * z * (2 * zz - 3 * xx - 3 * yy) * sh[..., 12]
+                          + SH_C3[4] * x * (4 * zz - xx - yy) * sh[..., 13] + SH_C3[5] * z * (xx - yy) * sh[..., 14]
+                          + SH_C3[6] * x * (xx - 3 * yy) * sh[..., 15])
+    return result
+
+
+def python_sh_colors(features, xyz, campos, active_sh_degree, max_sh_degree=3):
+    """gaussian_renderer/__init__.py:269-274 (pipe.convert_SHs_python)"""
+    shs_view = features.transpose(1, 2).view(-1, 3, (max_sh_degree + 1) ** 2)
+    dir_pp = xyz - campos.repeat(features.shape[0], 1)
+    dir_pp_normalized = dir_pp / dir_pp.norm(dim=1, keepdim=True)
+    return torch.clamp_min(eval_sh(active_sh_degree, shs_view, dir_pp_normalized) + 0.5, 0.0)
+
+
+def python_language_feature(language_feature):
+    """gaussian_renderer/__init__.py:281-287"""
+    sh2language = eval_sh(0, language_feature.view(-1, 3, 1), None)
+    return sh2language / (sh2language.norm(dim=-1, keepdim=True) + 1e-9)

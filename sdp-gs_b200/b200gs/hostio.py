@@ -31,6 +31,9 @@ class PinnedFeeder:
             self.host[o:o + n].copy_(torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32).reshape(-1)))
         self.nbytes = int(sum(n for _, n, _ in self.layout.values()) * 4)
         self.dev = [torch.empty((self.total,), dtype=torch.float32, device=self.device) for _ in range(2)]
+        # persistent leaf views (requires_grad) of the two device buffers: handing them out costs nothing per step
+        self.leaves = [{k: buf[o:o + n].view(shape).requires_grad_(True) for k, (o, n, shape) in self.layout.items()}
+                       for buf in self.dev]
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.filled = [torch.cuda.Event(), torch.cuda.Event()]   # copy into dev[i] finished
         self.released = [torch.cuda.Event(), torch.cuda.Event()]  # last reader of dev[i] finished
@@ -45,11 +48,13 @@ class PinnedFeeder:
     def _enqueue_copy(self, i):
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.released[i])
-            self.dev[i].copy_(self.host, non_blocking=True)
+            with torch.no_grad():
+                self.dev[i].copy_(self.host, non_blocking=True)
             self.filled[i].record(self.copy_stream)
 
     def next(self):
-        """Device tensors for this step (valid until the next-but-one call)."""
+        """Device tensors for this step (leaf tensors with requires_grad=True and .grad reset; valid until the
+        next-but-one call)."""
         cs = torch.cuda.current_stream(self.device)
         if not self._primed:
             for ev in self.released:
@@ -61,8 +66,9 @@ class PinnedFeeder:
         j = i ^ 1
         if self.prefetch:
             self._enqueue_copy(j)  # next step's upload overlaps this step's kernels
-        buf = self.dev[i]
-        out = {k: buf[o:o + n].view(shape) for k, (o, n, shape) in self.layout.items()}
+        out = self.leaves[i]
+        for v in out.values():
+            v.grad = None
         self._last = i
         self.cur = j
         return out

@@ -22,6 +22,7 @@ _CAPACITY = None
 
 _AUTO = {}      # (P, W, H, device) -> capacity learned from earlier forwards ("auto" mode)
 _PENDING = []   # [(event, pinned header copy, key)] status read-backs of earlier no-sync forwards, checked lazily
+_FREE_STATUS = []  # recycled (event, pinned 16-byte buffer) pairs
 
 
 def set_binning_capacity(capacity):
@@ -57,6 +58,7 @@ def _check_pending(block=False):
             _AUTO[key] = int(n * 1.3) + 4096
         if overflow & 1:
             err = _lib.B200GSError(f"binning capacity overflow in an earlier forward (num_rendered={n}); capacity re-learned")
+        _FREE_STATUS.append((ev, host))
     _PENDING[:] = keep
     if err is not None:
         raise err
@@ -75,15 +77,50 @@ def _f32c(t, name):
         raise RuntimeError(f"{name} must be a CUDA tensor (b200gs has no CPU path)")
     if t.dtype != torch.float32:
         t = t.float()
-    return t.contiguous()
+    return t if t.is_contiguous() else t.contiguous()
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _carve(flat, shapes, align=64):
+    """Views of one flat allocation (one allocator call instead of one per output); `align` in elements."""
+    out, off = [], 0
+    for shp in shapes:
+        n = 1
+        for d in shp:
+            n *= d
+        out.append(flat[off:off + n].view(shp))
+        off += (n + align - 1) // align * align
+    return out
+
+
+def _carve_size(shapes, align=64):
+    tot = 0
+    for shp in shapes:
+        n = 1
+        for d in shp:
+            n *= d
+        tot += (n + align - 1) // align * align
+    return tot
+
+
+def _stream(device=None):
+    """The raw cudaStream_t torch is currently launching on (a C call; torch.cuda.current_stream() costs ~10x more)."""
+    idx = torch.cuda.current_device() if device is None or device.index is None else device.index
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(idx))
 
 
 def _cpu_deep_copy_tuple(args):
     return tuple(a.detach().cpu().clone() if isinstance(a, torch.Tensor) else a for a in args)
+
+
+_WS_BYTES = {}
+
+
+def _ws_bytes(P, W, H):
+    k = (P, W, H)
+    v = _WS_BYTES.get(k)
+    if v is None:
+        v = _WS_BYTES[k] = (int(lib.b200gs_geom_bytes(P)), int(lib.b200gs_image_bytes(W, H)))
+    return v
 
 
 class _State:
@@ -133,20 +170,23 @@ def _forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations,
     v = _build_view(rs, P, M, extended, keep)
 
     f32 = dict(dtype=torch.float32, device=dev)
-    color = torch.empty((3, H, W), **f32)
     radii = torch.empty((P,), dtype=torch.int32, device=dev)
     depth = alpha = feature = None
     o = Outputs()
-    o.color, o.radii = color.data_ptr(), _ptr(radii)
-    if extended:
-        depth, alpha, feature = torch.empty((1, H, W), **f32), torch.empty((1, H, W), **f32), torch.empty((3, H, W), **f32)
+    if extended:  # one allocation for the four maps
+        shapes = ((3, H, W), (1, H, W), (1, H, W), (3, H, W))
+        color, depth, alpha, feature = _carve(torch.empty((_carve_size(shapes),), **f32), shapes)
         o.depth, o.alpha, o.feature = depth.data_ptr(), alpha.data_ptr(), feature.data_ptr()
+    else:
+        color = torch.empty((3, H, W), **f32)
+    o.color, o.radii = color.data_ptr(), _ptr(radii)
 
-    geom = torch.empty((lib.b200gs_geom_bytes(P),), dtype=torch.uint8, device=dev)
-    img = torch.empty((lib.b200gs_image_bytes(W, H),), dtype=torch.uint8, device=dev)
+    gb, ib = _ws_bytes(P, W, H)
+    wsbuf = torch.empty((gb + ib,), dtype=torch.uint8, device=dev)  # geom | image in one allocation (both 256-byte multiples)
+    geom, img = wsbuf[:gb], wsbuf[gb:]
     ws = Workspace()
-    ws.geom, ws.geom_bytes, ws.image, ws.image_bytes = geom.data_ptr(), geom.numel(), img.data_ptr(), img.numel()
-    stream = _stream()
+    ws.geom, ws.geom_bytes, ws.image, ws.image_bytes = geom.data_ptr(), gb, img.data_ptr(), ib
+    stream = _stream(dev)
     if P == 0:  # rasterize_points.cu:81: nothing is launched for an empty scene, outputs are zeros
         color.zero_()
         if extended:
@@ -171,9 +211,8 @@ def _forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations,
     ws.binning, ws.binning_bytes = binning.data_ptr(), binning.numel()
     check(lib.b200gs_forward_render(C.byref(v), C.byref(g), C.byref(o), C.byref(ws), C.c_int64(capacity), stream))
     if auto_key is not None:  # asynchronous read-back of {num_rendered, overflow}; looked at by a later call
-        host = torch.empty((16,), dtype=torch.uint8, pin_memory=True)
+        ev, host = _FREE_STATUS.pop() if _FREE_STATUS else (torch.cuda.Event(), torch.empty((16,), dtype=torch.uint8, pin_memory=True))
         host.copy_(geom[:16], non_blocking=True)
-        ev = torch.cuda.Event()
         ev.record()
         _PENDING.append((ev, host, auto_key))
     del keep
@@ -189,20 +228,19 @@ def _backward_impl(rs, num_rendered, capacity, extended, means3D, sh, colors_pre
     M = 0 if (sh is None or sh.numel() == 0) else int(sh.shape[1])
     f32 = dict(dtype=torch.float32, device=dev)
     has = lambda t: t is not None and t.numel() != 0
-    # every buffer is fully written by the kernels (zeros where radii == 0): no torch.zeros fills
-    d_means3D = torch.empty((P, 3), **f32)
-    d_means2D = torch.empty((P, 3), **f32)
-    d_opac = torch.empty((P, 1), **f32)
-    d_sh = torch.empty((P, M, 3), **f32) if has(sh) else None
-    d_colors = torch.empty((P, 3), **f32) if has(colors_precomp) else None
-    d_scales = torch.empty((P, 3), **f32) if has(scales) else None
-    d_rots = torch.empty((P, 4), **f32) if has(rotations) else None
-    d_cov = torch.empty((P, 6), **f32) if has(cov3Ds_precomp) else None
-    d_feat = torch.empty((P, 3), **f32) if (extended and has(language_feature_precomp)) else None
-    d_shl = torch.empty(tuple(shs_language.shape), **f32) if (extended and has(shs_language)) else None
+    # every buffer is fully written by the kernels (zeros where radii == 0): no torch.zeros fills.  One allocation, carved.
+    want = [("means3D", (P, 3), True), ("means2D", (P, 3), True), ("opac", (P, 1), True), ("sh", (P, M, 3), has(sh)),
+            ("colors", (P, 3), has(colors_precomp)), ("scales", (P, 3), has(scales)), ("rots", (P, 4), has(rotations)),
+            ("cov", (P, 6), has(cov3Ds_precomp)), ("feat", (P, 3), extended and has(language_feature_precomp)),
+            ("shl", tuple(shs_language.shape) if has(shs_language) else (P, 3), extended and has(shs_language)),
+            ("scratch", (P, 16), P > 0)]
+    shapes = [shp for _, shp, on in want if on]
+    views = iter(_carve(torch.empty((max(_carve_size(shapes), 1),), **f32), shapes))
+    got = {name: (next(views) if on else None) for name, _, on in want}
+    d_means3D, d_means2D, d_opac, d_sh, d_colors = got["means3D"], got["means2D"], got["opac"], got["sh"], got["colors"]
+    d_scales, d_rots, d_cov, d_feat, d_shl, scratch = got["scales"], got["rots"], got["cov"], got["feat"], got["shl"], got["scratch"]
     if P == 0:
         return d_means3D, d_means2D, d_sh, d_colors, d_opac, d_scales, d_rots, d_cov, d_shl, d_feat
-    scratch = torch.empty((lib.b200gs_scratch_bytes(P),), dtype=torch.uint8, device=dev)
 
     g = Gaussians()
     g.P = P
@@ -222,7 +260,7 @@ def _backward_impl(rs, num_rendered, capacity, extended, means3D, sh, colors_pre
     gr.dL_dopacities, gr.dL_dscales, gr.dL_drotations, gr.dL_dcov3D = _ptr(d_opac), _ptr(d_scales), _ptr(d_rots), _ptr(d_cov)
     gr.dL_dfeatures, gr.dL_dshs_language, gr.scratch = _ptr(d_feat), _ptr(d_shl), scratch.data_ptr()
     check(lib.b200gs_backward(C.byref(v), C.byref(g), radii.data_ptr(), C.byref(ws), C.c_int64(capacity), C.byref(go),
-                              C.byref(gr), _stream()))
+                              C.byref(gr), _stream(dev)))
     del keep
     return d_means3D, d_means2D, d_sh, d_colors, d_opac, d_scales, d_rots, d_cov, d_shl, d_feat
 

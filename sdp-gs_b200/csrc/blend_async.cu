@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(32) blend_forward_async_kernel(
 			uint32_t ps[4];
 #pragma unroll
 			for (int k = 0; k < 4; k++) {
-				const int s = start + ((k0 + k) & 31);
+				const int s = start + min(k0 + k, count - 1);  // past the end: re-read the last staged survivor (weight 0) -- never a stale slot, whose bits may be NaN
 				const float4 a = s_g0[s];
 				const float4 b = s_g1[s];
 				cc[k] = s_g2[s];

@@ -195,10 +195,11 @@ __global__ void __launch_bounds__(32 * NW) blend_forward_pipe_kernel(
 #pragma unroll
 			for (int k = 0; k < 4; k++) {
 				const bool v = k0 + k < cnt;
+				const int kk = min(k0 + k, cnt - 1);  // never a stale slot (its bits may be NaN; weight-0 accumulation needs finite payloads)
 				al[k] = v ? s_alpha[w][k0 + k][lane] : 0.f;
-				cc[k] = s_g2[w][(k0 + k) & 31];
-				if (EXT) ff[k] = s_g3[w][(k0 + k) & 31];
-				ps[k] = __float_as_uint(s_g1[w][(k0 + k) & 31].w);
+				cc[k] = s_g2[w][kk];
+				if (EXT) ff[k] = s_g3[w][kk];
+				ps[k] = __float_as_uint(s_g1[w][kk].w);
 			}
 #pragma unroll
 			for (int k = 0; k < 4; k++) {
