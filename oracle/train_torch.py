@@ -132,3 +132,123 @@ def python_language_feature(language_feature):
     """gaussian_renderer/__init__.py:281-287"""
     sh2language = eval_sh(0, language_feature.view(-1, 3, 1), None)
     return sh2language / (sh2language.norm(dim=-1, keepdim=True) + 1e-9)
+
+
+# ---- scene/gaussian_model.py:400-608: densification on nn.Parameters + the torch optimizer state (restated; proximity()
+# is left out because simple_knn is not vendored -- SURVEY.md F5)
+class DensifyModel:
+    """The slice of GaussianModel that densify_and_prune touches.  `raw`: dict of tensors xyz, f_dc [P,1,3], f_rest
+    [P,15,3], opacity, scaling, rotation, feature; `state`: dict name -> (exp_avg, exp_avg_sq) or None."""
+    NAMES = ("xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation", "feature")
+
+    def __init__(self, raw, hp, moments=None, percent_dense=0.01, prune_from_iter=500):
+        from torch import nn
+        self.p = {k: nn.Parameter(raw[k].clone().requires_grad_(True)) for k in self.NAMES}
+        self.optimizer = make_optimizer(self.p, hp)
+        self.group_of = {"language_feature": "feature"}
+        if moments is not None:
+            for g in self.optimizer.param_groups:
+                k = self.group_of.get(g["name"], g["name"])
+                self.optimizer.state[g["params"][0]] = {"step": torch.tensor(0.0), "exp_avg": moments[k][0].clone(),
+                                                        "exp_avg_sq": moments[k][1].clone()}
+        self.percent_dense, self.prune_from_iter = percent_dense, prune_from_iter
+        P = raw["xyz"].shape[0]
+        dev = raw["xyz"].device
+        self.xyz_gradient_accum = torch.zeros((P, 1), device=dev)
+        self.denom = torch.zeros((P, 1), device=dev)
+        self.max_radii2D = torch.zeros((P,), device=dev)
+
+    get_scaling = property(lambda self: torch.exp(self.p["scaling"]))
+    get_opacity = property(lambda self: torch.sigmoid(self.p["opacity"]))
+
+    def _key(self, group):
+        return self.group_of.get(group["name"], group["name"])
+
+    def _prune_optimizer(self, mask):
+        from torch import nn
+        for group in self.optimizer.param_groups:
+            stored = self.optimizer.state.get(group["params"][0], None)
+            if stored is not None:
+                stored["exp_avg"] = stored["exp_avg"][mask]
+                stored["exp_avg_sq"] = stored["exp_avg_sq"][mask]
+                del self.optimizer.state[group["params"][0]]
+                group["params"][0] = nn.Parameter(group["params"][0][mask].requires_grad_(True))
+                self.optimizer.state[group["params"][0]] = stored
+            else:
+                group["params"][0] = nn.Parameter(group["params"][0][mask].requires_grad_(True))
+            self.p[self._key(group)] = group["params"][0]
+
+    def prune_points(self, mask, it):
+        if it > self.prune_from_iter:
+            valid = ~mask
+            self._prune_optimizer(valid)
+            self.xyz_gradient_accum = self.xyz_gradient_accum[valid]
+            self.denom = self.denom[valid]
+            self.max_radii2D = self.max_radii2D[valid]
+
+    def cat_tensors_to_optimizer(self, d):
+        from torch import nn
+        for group in self.optimizer.param_groups:
+            ext = d[self._key(group)]
+            stored = self.optimizer.state.get(group["params"][0], None)
+            if stored is not None:
+                stored["exp_avg"] = torch.cat((stored["exp_avg"], torch.zeros_like(ext)), dim=0)
+                stored["exp_avg_sq"] = torch.cat((stored["exp_avg_sq"], torch.zeros_like(ext)), dim=0)
+                del self.optimizer.state[group["params"][0]]
+                group["params"][0] = nn.Parameter(torch.cat((group["params"][0], ext), dim=0).requires_grad_(True))
+                self.optimizer.state[group["params"][0]] = stored
+            else:
+                group["params"][0] = nn.Parameter(torch.cat((group["params"][0], ext), dim=0).requires_grad_(True))
+            self.p[self._key(group)] = group["params"][0]
+
+    def densification_postfix(self, d):
+        self.cat_tensors_to_optimizer(d)
+        P, dev = self.p["xyz"].shape[0], self.p["xyz"].device
+        self.xyz_gradient_accum = torch.zeros((P, 1), device=dev)
+        self.denom = torch.zeros((P, 1), device=dev)
+        self.max_radii2D = torch.zeros((P,), device=dev)
+
+    @staticmethod
+    def build_rotation(r):
+        norm = torch.sqrt(r[:, 0] * r[:, 0] + r[:, 1] * r[:, 1] + r[:, 2] * r[:, 2] + r[:, 3] * r[:, 3])
+        q = r / norm[:, None]
+        R = torch.zeros((q.size(0), 3, 3), device=r.device)
+        r_, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+        R[:, 0, 0] = 1 - 2 * (y * y + z * z); R[:, 0, 1] = 2 * (x * y - r_ * z); R[:, 0, 2] = 2 * (x * z + r_ * y)
+        R[:, 1, 0] = 2 * (x * y + r_ * z); R[:, 1, 1] = 1 - 2 * (x * x + z * z); R[:, 1, 2] = 2 * (y * z - r_ * x)
+        R[:, 2, 0] = 2 * (x * z - r_ * y); R[:, 2, 1] = 2 * (y * z + r_ * x); R[:, 2, 2] = 1 - 2 * (x * x + y * y)
+        return R
+
+    def densify_and_split(self, grads, grad_threshold, scene_extent, it, N=2, generator=None):
+        n_init = self.p["xyz"].shape[0]
+        padded = torch.zeros((n_init,), device=grads.device)
+        padded[:grads.shape[0]] = grads.squeeze()
+        sel = torch.where(padded >= grad_threshold, True, False)
+        sel = torch.logical_and(sel, torch.max(self.get_scaling, dim=1).values > self.percent_dense * scene_extent)
+        stds = self.get_scaling[sel].repeat(N, 1)
+        means = torch.zeros((stds.size(0), 3), device=grads.device)
+        samples = torch.normal(mean=means, std=stds, generator=generator)
+        rots = self.build_rotation(self.p["rotation"][sel]).repeat(N, 1, 1)
+        d = dict(xyz=torch.bmm(rots, samples.unsqueeze(-1)).squeeze(-1) + self.p["xyz"][sel].repeat(N, 1),
+                 scaling=torch.log(self.get_scaling[sel].repeat(N, 1) / (0.8 * N)), rotation=self.p["rotation"][sel].repeat(N, 1),
+                 f_dc=self.p["f_dc"][sel].repeat(N, 1, 1), f_rest=self.p["f_rest"][sel].repeat(N, 1, 1),
+                 opacity=self.p["opacity"][sel].repeat(N, 1), feature=self.p["feature"][sel].repeat(N, 1))
+        self.densification_postfix(d)
+        self.prune_points(torch.cat((sel, torch.zeros(N * int(sel.sum()), device=grads.device, dtype=bool))), it)
+
+    def densify_and_clone(self, grads, grad_threshold, scene_extent):
+        sel = torch.where(torch.norm(grads, dim=-1) >= grad_threshold, True, False)
+        sel = torch.logical_and(sel, torch.max(self.get_scaling, dim=1).values <= self.percent_dense * scene_extent)
+        self.densification_postfix({k: self.p[k][sel] for k in self.NAMES})
+
+    def densify_and_prune(self, max_grad, min_opacity, extent, max_screen_size, it, generator=None):
+        grads = self.xyz_gradient_accum / self.denom
+        grads[grads.isnan()] = 0.0
+        self.densify_and_clone(grads, max_grad, extent)
+        self.densify_and_split(grads, max_grad, extent, it, generator=generator)
+        prune_mask = (self.get_opacity < min_opacity).squeeze()
+        if max_screen_size:
+            big_vs = self.max_radii2D > max_screen_size
+            big_ws = self.get_scaling.max(dim=1).values > 0.1 * extent
+            prune_mask = torch.logical_or(torch.logical_or(prune_mask, big_vs), big_ws)
+        self.prune_points(prune_mask, it)

@@ -90,23 +90,24 @@ class FusedGradBuffer:
     def __init__(self, P, device, sh_coeffs=16, symmetric=None):
         assert sh_coeffs == 16, "segment table assumes max_sh_degree = 3 (arguments/__init__.py:49)"
         self.P = P
+        Pp = self.Pp = (P + 3) // 4 * 4  # segment stride: every segment starts 16-byte aligned whatever P is
         self.flat = None
         self._symm = None
         rank, n = world()
         mode = os.environ.get("B200GS_ALLREDUCE", "auto")
         if symmetric is None:
-            symmetric = n > 1 and torch.device(device).type == "cuda" and mode != "nccl" and (62 * P) % 4 == 0
+            symmetric = n > 1 and torch.device(device).type == "cuda" and mode != "nccl"
         if symmetric:
-            self._symm = _SymmetricBuffer.create(P * FUSED_WIDTH, device, mode)
+            self._symm = _SymmetricBuffer.create(Pp * FUSED_WIDTH, device, mode)
             if self._symm is not None:
                 self.flat = self._symm.tensor
         if self.flat is None:
-            self.flat = torch.zeros((P * FUSED_WIDTH,), dtype=torch.float32, device=device)
+            self.flat = torch.zeros((Pp * FUSED_WIDTH,), dtype=torch.float32, device=device)
         self.max_radii2D = torch.zeros((P,), dtype=torch.int32, device=device)
         self.seg = {}
         c = 0
         for name, w in SLOTS:
-            self.seg[name] = self.flat[c * P:(c + w) * P].view(P, w)
+            self.seg[name] = self.flat[c * Pp:c * Pp + w * P].view(P, w)
             c += w
         self.seg["shs"] = self.seg["shs"].view(P, 16, 3)
 
@@ -139,11 +140,11 @@ class FusedGradBuffer:
     @property
     def grads_flat(self):
         """The 62 parameter-gradient floats per Gaussian (everything before the two statistics segments)."""
-        return self.flat[: 62 * self.P]
+        return self.flat[: 62 * self.Pp]
 
     @property
     def stats_flat(self):
-        return self.flat[62 * self.P:]
+        return self.flat[62 * self.Pp:]
 
     def all_reduce(self, async_op=False, with_statistics=False):
         """SUM over ranks of the parameter gradients: ONE collective per training step.  The densification
@@ -155,7 +156,7 @@ class FusedGradBuffer:
             return None
         if self._symm is not None and not async_op:
             # our own kernel over NVLink peer memory (include/b200gs_collective.h), on the current stream
-            self._symm.all_reduce(0, (64 if with_statistics else 62) * self.P)
+            self._symm.all_reduce(0, (64 if with_statistics else 62) * self.Pp)
             if with_statistics:
                 dist.all_reduce(self.max_radii2D, op=dist.ReduceOp.MAX)
             return None

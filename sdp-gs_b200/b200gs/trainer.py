@@ -55,26 +55,6 @@ class GaussianTrainer:
                                         dtype=torch.float32).to(dev).contiguous()
         self.hp = dict(DEFAULTS)
         self.hp.update(hparams or {})
-        P = self.P = int(xyz.shape[0])
-        # raw parameters: one flat allocation of P*62 floats, Adam moments alike
-        self.widths = dict(xyz=3, shs=48, opacity=1, scaling=3, rotation=4, feature=3)
-        self.raw_flat = torch.zeros((P * 62,), dtype=torch.float32, device=dev)
-        self.m_flat = torch.zeros_like(self.raw_flat)
-        self.v_flat = torch.zeros_like(self.raw_flat)
-        self.raw, self.m, self.v = {}, {}, {}
-        c = 0
-        for k, w in self.widths.items():
-            for store, flat in ((self.raw, self.raw_flat), (self.m, self.m_flat), (self.v, self.v_flat)):
-                store[k] = flat[c * P:(c + w) * P].view(P, w)
-            c += w
-        self.raw["xyz"].copy_(f32(xyz)); self.raw["shs"].copy_(f32(shs).reshape(P, 48))
-        self.raw["opacity"].copy_(f32(opacity_raw).reshape(P, 1)); self.raw["scaling"].copy_(f32(scaling_raw))
-        self.raw["rotation"].copy_(f32(rotation_raw)); self.raw["feature"].copy_(f32(feature))
-        self.act = dict(opacity=torch.empty((P, 1), dtype=torch.float32, device=dev),
-                        scaling=torch.empty((P, 3), dtype=torch.float32, device=dev),
-                        rotation=torch.empty((P, 4), dtype=torch.float32, device=dev))
-        self.bucket = parallel.FusedGradBuffer(P, dev)
-        self.g_means2D = torch.zeros((P, 3), dtype=torch.float32, device=dev)
         self.cameras = list(cameras)
         self.gt = [f32(g) for g in gt_images]
         self.mono = [f32(d).reshape(-1) for d in depth_mono]
@@ -87,18 +67,47 @@ class GaussianTrainer:
         self.loss = torch.zeros((4,), dtype=torch.float64, device=dev)
         self.scratch = torch.empty((lib.b200gs_photometric_scratch_bytes(W, H) // 4,), dtype=torch.float32, device=dev)
         self.iteration = 0
+        self.capacity = capacity
+        self.settings_fn = settings_fn or self._default_settings
+        self.widths = dict(xyz=3, shs=48, opacity=1, scaling=3, rotation=4, feature=3)
+        P = int(xyz.shape[0])
+        self._allocate(dict(xyz=f32(xyz), shs=f32(shs).reshape(P, 48), opacity=f32(opacity_raw).reshape(P, 1), scaling=f32(scaling_raw),
+                            rotation=f32(rotation_raw), feature=f32(feature)))
         self.set_hparams(step=1)
         self._refresh_activations()
 
-        settings_fn = settings_fn or self._default_settings
+    def _allocate(self, raw, m=None, v=None):
+        """(Re)build every per-Gaussian buffer for the given raw parameters (and Adam moments): flat parameter / moment
+        allocations, activated copies, the fused gradient buffer and one RasterSession per view."""
+        dev = self.dev
+        P = self.P = int(raw["xyz"].shape[0])
+        Pp = (P + 3) // 4 * 4  # segment stride: 16-byte aligned segments for any P (128-bit accesses, TMA bulk copies)
+        self.raw_flat = torch.zeros((Pp * 62,), dtype=torch.float32, device=dev)
+        self.m_flat = torch.zeros_like(self.raw_flat)
+        self.v_flat = torch.zeros_like(self.raw_flat)
+        self.raw, self.m, self.v = {}, {}, {}
+        c = 0
+        for k, w in self.widths.items():
+            for store, flat in ((self.raw, self.raw_flat), (self.m, self.m_flat), (self.v, self.v_flat)):
+                store[k] = flat[c * Pp:c * Pp + w * P].view(P, w)
+            c += w
+        for k in self.widths:
+            self.raw[k].copy_(raw[k].reshape(P, self.widths[k]))
+            if m is not None:
+                self.m[k].copy_(m[k].reshape(P, self.widths[k])); self.v[k].copy_(v[k].reshape(P, self.widths[k]))
+        self.act = dict(opacity=torch.empty((P, 1), dtype=torch.float32, device=dev),
+                        scaling=torch.empty((P, 3), dtype=torch.float32, device=dev),
+                        rotation=torch.empty((P, 4), dtype=torch.float32, device=dev))
+        self.bucket = parallel.FusedGradBuffer(P, dev)
+        self.g_means2D = torch.zeros((P, 3), dtype=torch.float32, device=dev)
         grads_out = dict(means3D=self.bucket.segment("xyz"), shs=self.bucket.segment("shs"), opacities=self.bucket.segment("opacity"),
                          scales=self.bucket.segment("scaling"), rotations=self.bucket.segment("rotation"),
                          shs_language=self.bucket.segment("language_feature"), means2D=self.g_means2D)
         self.sessions = []
         for cam in self.cameras:
-            s = rz.RasterSession(settings_fn(cam), means3D=self.raw["xyz"], opacities=self.act["opacity"],
+            s = rz.RasterSession(self.settings_fn(cam), means3D=self.raw["xyz"], opacities=self.act["opacity"],
                                  shs=self.raw["shs"].view(P, 16, 3), scales=self.act["scaling"], rotations=self.act["rotation"],
-                                 shs_language=self.raw["feature"], extended=True, capacity=capacity, grads_out=grads_out)
+                                 shs_language=self.raw["feature"], extended=True, capacity=self.capacity, grads_out=grads_out)
             self.sessions.append(s)
         self.graphs = None
 
@@ -214,6 +223,91 @@ class GaussianTrainer:
         if gb is not None:
             self.bucket.all_reduce()
             gb.replay()
+
+    # ------------------------------------------------------------------ densification (host-side logic, every ~100 iterations)
+    @staticmethod
+    def _build_rotation(r):
+        """utils/general_utils.py:88-109"""
+        norm = torch.sqrt(r[:, 0] * r[:, 0] + r[:, 1] * r[:, 1] + r[:, 2] * r[:, 2] + r[:, 3] * r[:, 3])
+        q = r / norm[:, None]
+        R = torch.zeros((q.size(0), 3, 3), device=r.device)
+        r_, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+        R[:, 0, 0] = 1 - 2 * (y * y + z * z); R[:, 0, 1] = 2 * (x * y - r_ * z); R[:, 0, 2] = 2 * (x * z + r_ * y)
+        R[:, 1, 0] = 2 * (x * y + r_ * z); R[:, 1, 1] = 1 - 2 * (x * x + z * z); R[:, 1, 2] = 2 * (y * z - r_ * x)
+        R[:, 2, 0] = 2 * (x * z - r_ * y); R[:, 2, 1] = 2 * (y * z + r_ * x); R[:, 2, 2] = 1 - 2 * (x * x + y * y)
+        return R
+
+    def densify_and_prune(self, max_grad, min_opacity, extent, max_screen_size, iteration=None, percent_dense=0.01,
+                          prune_from_iter=500, N=2, generator=None, recapture=True):
+        """scene/gaussian_model.py:591-608 (densify_and_clone, densify_and_split, prune) on the trainer's buffers, in
+        the reference's order of operations and row order: [survivors of the old rows | clones | split copies].  New rows
+        get zero Adam moments (cat_tensors_to_optimizer), all statistics are reset (densification_postfix).  Every rank of
+        an image-parallel job calls this with the same arguments: the statistics are combined first, and torch.normal
+        draws from `generator` (or the global CUDA generator) -- seed it identically on every rank.
+        Not reproduced: proximity() (iteration < 2000), it needs the un-vendored simple_knn kNN.
+        Buffers are re-allocated and, with `recapture`, the per-view graphs are captured again."""
+        iteration = self.iteration if iteration is None else iteration
+        if parallel.world()[1] > 1:
+            self.bucket.all_reduce_statistics()
+        torch.cuda.synchronize(self.dev)
+        raw = {k: t.clone() for k, t in self.raw.items()}
+        m = {k: t.clone() for k, t in self.m.items()}
+        v = {k: t.clone() for k, t in self.v.items()}
+        accum, denom = self.bucket.segment("xyz_gradient_accum").clone(), self.bucket.segment("denom").clone()
+        grads = accum / denom
+        grads[grads.isnan()] = 0.0
+        get_scaling = lambda: torch.exp(raw["scaling"])
+
+        def cat(new):  # cat_tensors_to_optimizer + densification_postfix
+            for k in raw:
+                raw[k] = torch.cat((raw[k], new[k]), dim=0)
+                m[k] = torch.cat((m[k], torch.zeros_like(new[k])), dim=0)
+                v[k] = torch.cat((v[k], torch.zeros_like(new[k])), dim=0)
+
+        def prune(mask):  # prune_points: keep ~mask
+            if iteration > prune_from_iter:
+                keep = ~mask
+                for k in raw:
+                    raw[k], m[k], v[k] = raw[k][keep], m[k][keep], v[k][keep]
+
+        # densify_and_clone
+        sel = torch.where(torch.norm(grads, dim=-1) >= max_grad, True, False)
+        sel = torch.logical_and(sel, torch.max(get_scaling(), dim=1).values <= percent_dense * extent)
+        cat({k: t[sel] for k, t in raw.items()})
+        # densify_and_split
+        n_init = raw["xyz"].shape[0]
+        padded = torch.zeros((n_init,), device=self.dev)
+        padded[:grads.shape[0]] = grads.squeeze()
+        sel = torch.where(padded >= max_grad, True, False)
+        sel = torch.logical_and(sel, torch.max(get_scaling(), dim=1).values > percent_dense * extent)
+        stds = get_scaling()[sel].repeat(N, 1)
+        means = torch.zeros((stds.size(0), 3), device=self.dev)
+        samples = torch.normal(mean=means, std=stds, generator=generator)
+        rots = self._build_rotation(raw["rotation"][sel]).repeat(N, 1, 1)
+        new = {k: t[sel].repeat(N, 1) for k, t in raw.items()}
+        new["xyz"] = torch.bmm(rots, samples.unsqueeze(-1)).squeeze(-1) + raw["xyz"][sel].repeat(N, 1)
+        new["scaling"] = torch.log(get_scaling()[sel].repeat(N, 1) / (0.8 * N))
+        cat(new)
+        prune(torch.cat((sel, torch.zeros(N * int(sel.sum()), device=self.dev, dtype=bool))))
+        # prune (max_radii2D was reset by densification_postfix, so the screen-size test sees zeros, as in the reference)
+        mask = (torch.sigmoid(raw["opacity"]) < min_opacity).squeeze()
+        if max_screen_size:
+            big_vs = torch.zeros((raw["xyz"].shape[0],), device=self.dev) > max_screen_size
+            big_ws = get_scaling().max(dim=1).values > 0.1 * extent
+            mask = torch.logical_or(torch.logical_or(mask, big_vs), big_ws)
+        prune(mask)
+        self._allocate(raw, m, v)
+        self._refresh_activations()
+        if recapture:
+            self.capture()
+        return self.P
+
+    def reset_opacity(self):
+        """scene/gaussian_model.py:351-355: opacity := inverse_sigmoid(min(opacity, 0.01)), its Adam moments zeroed."""
+        o = torch.min(torch.sigmoid(self.raw["opacity"]), torch.ones_like(self.raw["opacity"]) * 0.01)
+        self.raw["opacity"].copy_(torch.log(o / (1 - o)))
+        self.m["opacity"].zero_(); self.v["opacity"].zero_()
+        self._refresh_activations()
 
     def loss_values(self):
         """(total, L1, SSIM, weighted depth loss) of the last step."""

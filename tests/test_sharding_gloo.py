@@ -56,11 +56,12 @@ def test_shard_views_partition():
 
 def test_fused_buffer_layout():
     b = parallel.FusedGradBuffer(10, "cpu")
-    assert b.flat.numel() == 10 * 64 and parallel.FUSED_WIDTH == 64
-    # segments are contiguous tensors the rasterizer backward can write into directly
+    assert b.flat.numel() == 12 * 64 and parallel.FUSED_WIDTH == 64  # segment stride = P rounded up to a multiple of 4
+    # segments are contiguous, 16-byte aligned tensors the rasterizer backward can write into directly (any P)
     for name, w in parallel.SLOTS:
         seg = b.segment(name)
-        assert seg.is_contiguous() and seg.numel() == 10 * w
+        assert seg.is_contiguous() and seg.numel() == 10 * w and seg.data_ptr() % 16 == 0
+    assert b.grads_flat.numel() == 62 * 12 and b.stats_flat.numel() == 2 * 12
     b.segment("shs")[3, 2, 1] = 5.0
     assert b.flat.sum() == 5.0
 

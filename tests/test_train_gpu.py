@@ -300,3 +300,59 @@ def test_short_fit_lands_within_a_tenth_of_a_db_of_the_reference_pipeline():
     for a, b in zip(mine, ref):
         assert abs(a - b) <= 0.1, (mine, ref)
     assert min(mine) > start + 3.0  # and the fit actually went somewhere
+
+
+@gpu
+def test_densify_and_prune_matches_the_reference_procedure():
+    """GaussianTrainer.densify_and_prune against scene/gaussian_model.py:400-608 restated on nn.Parameters + the torch
+    optimizer state (oracle/train_torch.py::DensifyModel): same statistics, same RNG seed -> identical rows, row order
+    and Adam moments (everything is copied or computed by the same torch ops)."""
+    from b200gs.trainer import GaussianTrainer, DEFAULTS
+    from oracle import train_torch as tt
+    dev = torch.device("cuda", 0)
+    sc, cams, gts, monos, raw = _trainer_inputs("small", dev)
+    tr = GaussianTrainer(cameras=cams, gt_images=gts, depth_mono=monos, device=dev, capacity=400_000, **raw)
+    tr.capture()
+    for it in range(6):
+        tr.step(it % len(cams))
+    torch.cuda.synchronize()
+    P = tr.P
+    snap = {k: v.clone() for k, v in tr.raw.items()}
+    mom = {k: (tr.m[k].clone(), tr.v[k].clone()) for k in tr.raw}
+    accum, denom = tr.bucket.segment("xyz_gradient_accum").clone(), tr.bucket.segment("denom").clone()
+    assert float(denom.sum()) > 0
+    thr = float(torch.quantile((accum / denom.clamp_min(1)).squeeze(), 0.9))  # top 10 % densify
+    extent = 3.0
+    args = dict(max_grad=thr, min_opacity=0.05, extent=extent, max_screen_size=20)
+
+    model = tt.DensifyModel(dict(xyz=snap["xyz"], f_dc=snap["shs"].view(P, 16, 3)[:, :1], f_rest=snap["shs"].view(P, 16, 3)[:, 1:],
+                                 opacity=snap["opacity"], scaling=snap["scaling"], rotation=snap["rotation"], feature=snap["feature"]),
+                            dict(DEFAULTS),
+                            moments=dict(xyz=mom["xyz"], f_dc=tuple(t.view(P, 16, 3)[:, :1] for t in mom["shs"]),
+                                         f_rest=tuple(t.view(P, 16, 3)[:, 1:] for t in mom["shs"]), opacity=mom["opacity"],
+                                         scaling=mom["scaling"], rotation=mom["rotation"], feature=mom["feature"]))
+    model.xyz_gradient_accum, model.denom = accum.clone(), denom.clone()
+    g1 = torch.Generator(device=dev).manual_seed(1234)
+    model.densify_and_prune(it=1000, generator=g1, **args)
+
+    g2 = torch.Generator(device=dev).manual_seed(1234)
+    newP = tr.densify_and_prune(iteration=1000, generator=g2, **args)
+    assert newP == model.p["xyz"].shape[0] and newP != P
+    ref = dict(xyz=model.p["xyz"], shs=torch.cat((model.p["f_dc"], model.p["f_rest"]), 1).reshape(newP, 48), opacity=model.p["opacity"],
+               scaling=model.p["scaling"], rotation=model.p["rotation"], feature=model.p["feature"])
+    for k in tr.raw:
+        assert torch.equal(tr.raw[k], ref[k].detach()), k
+    st = {model._key(g): model.optimizer.state[g["params"][0]] for g in model.optimizer.param_groups}
+    m_ref = dict(xyz=st["xyz"]["exp_avg"], shs=torch.cat((st["f_dc"]["exp_avg"], st["f_rest"]["exp_avg"]), 1).reshape(newP, 48),
+                 opacity=st["opacity"]["exp_avg"], scaling=st["scaling"]["exp_avg"], rotation=st["rotation"]["exp_avg"],
+                 feature=st["feature"]["exp_avg"])
+    for k in tr.m:
+        assert torch.equal(tr.m[k], m_ref[k]), k
+    assert float(tr.bucket.segment("denom").sum()) == 0.0  # statistics reset
+    # and training goes on with the new Gaussian count
+    for it in range(3):
+        tr.step(it % len(cams))
+    torch.cuda.synchronize()
+    assert np.isfinite(tr.loss_values()[0])
+    tr.reset_opacity()
+    assert float(torch.sigmoid(tr.raw["opacity"]).max()) <= 0.01 + 1e-6
