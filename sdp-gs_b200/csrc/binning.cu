@@ -14,8 +14,8 @@
 // The radix pass is a single-read "onesweep" pass: per-tile digit counts are chained between
 // CTAs with decoupled look-back (one 32-bit status word per (tile, digit)), tile ids are handed
 // out by an atomic ticket so a CTA only ever waits on CTAs that already started.  The digit
-// histograms a pass needs are produced by the kernel that writes the keys (preprocess for the
-// depth keys, scan_emit for the tile keys), not by a separate read of the keys.
+// histograms of ALL passes are produced by the kernel that writes the keys (preprocess for the
+// depth keys, scan_emit for the tile keys), not by a separate read of the keys or inside the passes.
 #include <cstddef>
 #include "common.cuh"
 
@@ -107,8 +107,8 @@ template <int ITEMS>
 __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(
 	const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
 	uint32_t* __restrict__ vals_out, int64_t n_max, const unsigned long long* __restrict__ n_dev, int shift, int bits,
-	const uint32_t* __restrict__ hist /*[256] this pass*/, uint32_t* __restrict__ next_hist /*[256] next pass or null*/,
-	int next_shift, int next_bits, uint32_t* __restrict__ lookback /*[tiles][256]*/, unsigned int* __restrict__ ticket)
+	const uint32_t* __restrict__ hist /*[256] this pass: produced by the kernel that wrote the keys*/,
+	uint32_t* __restrict__ lookback /*[tiles][256]*/, unsigned int* __restrict__ ticket)
 {
 	constexpr int TILE = SORT_THREADS * ITEMS;
 	constexpr int WARPS = SORT_THREADS / 32;
@@ -118,14 +118,12 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(
 	__shared__ uint32_t s_keys[TILE];
 	__shared__ uint32_t s_vals[TILE];
 	__shared__ uint32_t s_g[WARPS], s_l[WARPS];
-	__shared__ uint32_t s_next[256];
 	__shared__ uint32_t s_tile;
 	__shared__ int s_trivial;
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	pdl_trigger();
 	for (int i = tid; i < WARPS * 256; i += SORT_THREADS) (&s_warp_hist[0][0])[i] = 0;
-	s_next[tid] = 0;
 	pdl_wait();
 	const int64_t n = load_count(n_dev, n_max);
 	if (tid == 0) { s_tile = atomicAdd(ticket, 1u); s_trivial = 0; }
@@ -136,7 +134,6 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(
 	if (tile_base >= n) return;
 	const int tile_n = (int)min((int64_t)TILE, n - tile_base);
 	const uint32_t dmask = (1u << bits) - 1;
-	const uint32_t nmask = (1u << next_bits) - 1;
 
 	// 1. load (warp-striped: warp w owns a contiguous 32*ITEMS chunk) and rank within the warp
 	uint32_t key[ITEMS], val[ITEMS], rnk[ITEMS];
@@ -147,10 +144,8 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(
 		const bool valid = li < tile_n;
 		key[j] = valid ? __ldcg(keys_in + tile_base + li) : 0xFFFFFFFFu;  // .cg, never .nc: see the note on pdl_wait() in common.cuh
 		val[j] = valid ? __ldcg(vals_in + tile_base + li) : 0u;
-		if (valid && next_hist != nullptr) atomicAdd(&s_next[(key[j] >> next_shift) & nmask], 1u);
 	}
-	__syncthreads();
-	if (next_hist != nullptr && s_next[tid]) atomicAdd(next_hist + tid, s_next[tid]);
+	__syncthreads();  // s_trivial settled
 	if (s_trivial) {
 #pragma unroll
 		for (int j = 0; j < ITEMS; j++) {
@@ -231,7 +226,6 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(
 // Also: digit histograms of the tile ids for the tile sort, and the zeroing of its look-back words.
 constexpr int EMIT_THREADS = SCAN_THREADS;
 constexpr int EMIT_ITEMS = SCAN_ITEMS;
-constexpr uint32_t EMIT_SMALL = 12;
 
 // TILE_COUNTS (images of at most COUNT_TILES_MAX tiles): every emitted instance is also counted into its tile, in
 // shared memory, and each CTA adds its non-zero counters to a global per-tile array (one counter per 128-byte
@@ -254,7 +248,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(
 	__shared__ uint32_t s_prefix;
 	__shared__ uint32_t s_tile;
 	__shared__ bool s_last;
-	__shared__ uint32_t s_ph[4][256];  // !TILE_COUNTS: [0] = first digit of the tile ids.  TILE_COUNTS, last CTA: digit histograms of all passes
+	__shared__ uint32_t s_ph[4][256];  // digit histograms of the tile-sort passes (TILE_COUNTS: built by the last CTA from the tile counts)
 	__shared__ uint32_t s_cnt[128], s_off[128];
 	__shared__ uint32_t s_tc[TILE_COUNTS ? COUNT_TILES_MAX : 1];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -313,34 +307,45 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(
 			keys[pos] = key;
 			vals[pos] = val;
 			if (TILE_COUNTS) atomicAdd(&s_tc[key], 1u);
-			else atomicAdd(&s_ph[0][key & m0], 1u);
-		}
-	};
-#pragma unroll
-	for (int k = 0; k < EMIT_ITEMS; k++) {
-		if (n[k] > 0 && n[k] <= EMIT_SMALL) {
-			uint32_t x = r[k].x, y = r[k].y;
-			for (uint32_t j = 0; j < n[k]; j++) {
-				put(start + j, y * grid_x + x, g[k]);
-				if (++x == r[k].z) { x = r[k].x; y++; }
+			else {
+				atomicAdd(&s_ph[0][key & m0], 1u);
+				if (tile_bits > 8) atomicAdd(&s_ph[1][(key >> 8) & 255u], 1u);
+				if (tile_bits > 16) { atomicAdd(&s_ph[2][(key >> 16) & 255u], 1u); if (tile_bits > 24) atomicAdd(&s_ph[3][key >> 24], 1u); }
 			}
 		}
-		// large footprints: the whole warp emits one Gaussian's tiles together
-		uint32_t big = __ballot_sync(0xFFFFFFFFu, n[k] > EMIT_SMALL);
-		while (big) {
-			const int src = __ffs(big) - 1;
-			big &= big - 1;
-			const uint32_t bg = __shfl_sync(0xFFFFFFFFu, g[k], src), bn = __shfl_sync(0xFFFFFFFFu, n[k], src);
-			const uint32_t bstart = __shfl_sync(0xFFFFFFFFu, start, src);
-			const uint32_t bx0 = __shfl_sync(0xFFFFFFFFu, (uint32_t)r[k].x, src), by0 = __shfl_sync(0xFFFFFFFFu, (uint32_t)r[k].y, src);
-			const uint32_t bw = __shfl_sync(0xFFFFFFFFu, (uint32_t)(r[k].z - r[k].x), src);
-			for (uint32_t j = lane; j < bn; j += 32) put(bstart + j, (by0 + j / bw) * grid_x + (bx0 + j % bw), bg);
+	};
+	// Slot-major emission: lane l of a warp writes output slots wbase + l, wbase + 32 + l, ... and finds the Gaussian that
+	// owns a slot by a binary search over the warp's 32 exclusive offsets (shuffles, no shared memory).  Every store
+	// instruction covers 32 consecutive slots (4 sectors) whatever the footprints are; the per-thread version wrote one
+	// Gaussian's run per lane and touched ~12 sectors per request (ncu at L = 48 M: 6x write amplification, 500 us).
+	static_assert(EMIT_ITEMS == 1, "slot-major emission assumes one Gaussian per thread");
+	{
+		const uint32_t wbase = __shfl_sync(0xFFFFFFFFu, start, 0);
+		const uint32_t rel = start - wbase;  // non-decreasing over the lanes
+		const uint32_t T = __shfl_sync(0xFFFFFFFFu, rel + n[0], 31);
+		const uint32_t rw = (uint32_t)(r[0].z - r[0].x);
+		for (uint32_t j0 = 0; j0 < T; j0 += 32) {
+			const uint32_t j = j0 + lane;
+			int lo = 0, hi = 32;  // the last lane whose offset is <= j owns slot j (empty lanes share the offset of their successor)
+#pragma unroll
+			for (int it = 0; it < 5; it++) {
+				const int mid = (lo + hi) >> 1;
+				const uint32_t v = __shfl_sync(0xFFFFFFFFu, rel, mid);
+				if (v <= j) lo = mid; else hi = mid;
+			}
+			const uint32_t og = __shfl_sync(0xFFFFFFFFu, g[0], lo);
+			const uint32_t ox = __shfl_sync(0xFFFFFFFFu, (uint32_t)r[0].x, lo), oy = __shfl_sync(0xFFFFFFFFu, (uint32_t)r[0].y, lo);
+			const uint32_t ow = __shfl_sync(0xFFFFFFFFu, rw, lo);
+			const uint32_t local = j - __shfl_sync(0xFFFFFFFFu, rel, lo);
+			if (j < T) put(wbase + j, (oy + local / ow) * grid_x + (ox + local % ow), og);
 		}
-		start += n[k];
 	}
 	__syncthreads();
 	if (!TILE_COUNTS) {
-		if (tid < 256 && s_ph[0][tid]) atomicAdd(tile_hist + tid, s_ph[0][tid]);
+		for (int i = tid; i < 256 * ((tile_bits + 7) / 8); i += EMIT_THREADS) {
+			const uint32_t c = (&s_ph[0][0])[i];
+			if (c) atomicAdd(tile_hist + i, c);
+		}
 		return;
 	}
 	// ---- the last CTA to get here turns the tile counts into: tile ranges (identifyTileRanges,
@@ -415,14 +420,31 @@ __global__ void __launch_bounds__(256) tile_ranges_schedule_kernel(
 	pdl_trigger();
 	pdl_wait();
 	const int64_t n = load_count(n_dev, n_max);
-	for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
-		const uint32_t cur = __ldcg(tile_keys + idx);
-		if (idx == 0) ranges[cur].x = 0;
-		else {
-			const uint32_t prev = __ldcg(tile_keys + idx - 1);
-			if (cur != prev) { ranges[prev].y = (uint32_t)idx; ranges[cur].x = (uint32_t)idx; }
+	// four consecutive keys per thread and step (one 128-bit load + the key before them): ncu showed the one-key version
+	// latency bound (long_scoreboard 50 stalls per issue, 12 % of DRAM peak at L = 48 M)
+	const int64_t n4 = (n + 3) / 4;
+	for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) {
+		const int64_t i0 = 4 * q;
+		uint32_t k[4];
+		if (i0 + 3 < n) {
+			const uint4 v = __ldcg(reinterpret_cast<const uint4*>(tile_keys) + q);
+			k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w;
+		} else {
+#pragma unroll
+			for (int j = 0; j < 4; j++) k[j] = i0 + j < n ? __ldcg(tile_keys + i0 + j) : 0u;
 		}
-		if (idx == n - 1) ranges[cur].y = (uint32_t)n;
+		uint32_t prev = i0 > 0 ? __ldcg(tile_keys + i0 - 1) : 0u;
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const int64_t idx = i0 + j;
+			if (idx < n) {
+				const uint32_t cur = k[j];
+				if (idx == 0) ranges[cur].x = 0;
+				else if (cur != prev) { ranges[prev].y = (uint32_t)idx; ranges[cur].x = (uint32_t)idx; }
+				if (idx == n - 1) ranges[cur].y = (uint32_t)n;
+				prev = cur;
+			}
+		}
 	}
 	__shared__ bool s_last;
 	__shared__ uint32_t s_cnt[128];
@@ -468,7 +490,7 @@ int tile_count_stride() { return COUNT_STRIDE; }
 
 int launch_radix_sort(uint32_t* key_a, uint32_t* key_b, uint32_t* val_a, uint32_t* val_b, int64_t n_max,
                       const unsigned long long* n_dev, int end_bit, uint32_t* hist, uint32_t* lookback,
-                      unsigned int* tickets, cudaStream_t stream, bool hist_ready) {
+                      unsigned int* tickets, cudaStream_t stream) {
 	if (n_max <= 0 || end_bit <= 0) return 0;
 	const int passes = (end_bit + 7) / 8;
 	const int items = sort_items_for(n_max);
@@ -476,17 +498,13 @@ int launch_radix_sort(uint32_t* key_a, uint32_t* key_b, uint32_t* val_a, uint32_
 	uint32_t *ki = key_a, *ko = key_b, *vi = val_a, *vo = val_b;
 	for (int p = 0; p < passes; p++) {
 		const int bits = end_bit - 8 * p < 8 ? end_bit - 8 * p : 8;
-		const bool more = p + 1 < passes;
-		const int nbits = more ? (end_bit - 8 * (p + 1) < 8 ? end_bit - 8 * (p + 1) : 8) : 1;
-		// histogram of the next pass's digit, taken while this pass reads the keys (unless the caller already has all of them)
-		uint32_t* nh = (more && !hist_ready) ? hist + 256 * (p + 1) : nullptr;
 		uint32_t* lb = lookback + (size_t)p * tiles * 256;
 		if (items == SORT_ITEMS_SMALL)
 			launch_k(PDL_SORT, onesweep_pass_kernel<SORT_ITEMS_SMALL>, dim3((unsigned)tiles), dim3(SORT_THREADS), stream,
-				ki, vi, ko, vo, n_max, n_dev, 8 * p, bits, hist + 256 * p, nh, 8 * (p + 1), nbits, lb, tickets + p);
+				ki, vi, ko, vo, n_max, n_dev, 8 * p, bits, hist + 256 * p, lb, tickets + p);
 		else
 			launch_k(PDL_SORT, onesweep_pass_kernel<SORT_ITEMS_LARGE>, dim3((unsigned)tiles), dim3(SORT_THREADS), stream,
-				ki, vi, ko, vo, n_max, n_dev, 8 * p, bits, hist + 256 * p, nh, 8 * (p + 1), nbits, lb, tickets + p);
+				ki, vi, ko, vo, n_max, n_dev, 8 * p, bits, hist + 256 * p, lb, tickets + p);
 		count_launch();
 		uint32_t* t = ki; ki = ko; ko = t;
 		t = vi; vi = vo; vo = t;
@@ -499,7 +517,7 @@ void launch_depth_order(GeomState& gs, int P, cudaStream_t stream) {
 	if (P <= 0) return;
 	// keys: key_a, values: order (identity), digit histograms gs.hist[0..3]: all written by preprocess; 4 passes -> result in (key_a, order)
 	unsigned int* tickets = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(gs.hdr) + offsetof(GeomHeader, sort_ticket));
-	launch_radix_sort(gs.key_a, gs.key_b, gs.order, gs.val_b, P, nullptr, 32, gs.hist, gs.lookback, tickets, stream, false);
+	launch_radix_sort(gs.key_a, gs.key_b, gs.order, gs.val_b, P, nullptr, 32, gs.hist, gs.lookback, tickets, stream);
 }
 
 void launch_scan_emit(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is, int P, int64_t capacity, cudaStream_t stream, bool chained) {
@@ -527,7 +545,7 @@ void launch_tile_sort(const b200gs_view_t& v, GeomState& gs, BinningState& bs, i
 	const unsigned long long* n_dev = &gs.hdr->num_rendered;
 	unsigned int* tickets = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(gs.hdr) + offsetof(GeomHeader, sort_ticket)) + 4;
 	const int where = launch_radix_sort(bs.key_a, bs.key_b, bs.val_a, bs.val_b, capacity, n_dev, bit, gs.hist + 4 * 256,
-	                                    bs.lookback, tickets, stream, tile_counts_path((int)(gx * gy)));
+	                                    bs.lookback, tickets, stream);
 	bs.sorted_keys = where ? bs.key_b : bs.key_a;
 	bs.sorted_vals = where ? bs.val_b : bs.val_a;
 }
@@ -537,7 +555,8 @@ void launch_tile_ranges(const b200gs_view_t& v, GeomState& gs, BinningState& bs,
 	const int tiles = ((v.width + TILE_X - 1) / TILE_X) * ((v.height + TILE_Y - 1) / TILE_Y);
 	const int64_t n_max = capacity > 0 ? capacity : 0;
 	// few CTAs (grid-stride): every CTA ends with one atomic on the same counter
-	const unsigned grid = (unsigned)(n_max > 0 ? (n_max + 255) / 256 < 148 * 4 ? (n_max + 255) / 256 : 148 * 4 : 1);
+	const int64_t chunks = (n_max + 1023) / 1024;  // 256 threads x 4 keys
+	const unsigned grid = (unsigned)(n_max > 0 ? (chunks < 148 * 8 ? chunks : 148 * 8) : 1);
 	unsigned int* counter = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(gs.hdr) + offsetof(GeomHeader, ranges_done));
 	launch_k(PDL_RANGES, tile_ranges_schedule_kernel, dim3(grid), dim3(256), stream, (const uint32_t*)bs.sorted_keys, n_max, n_dev, is.ranges, tiles, is.tile_order, counter);
 	count_launch();

@@ -98,7 +98,7 @@ void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, u
 // holds the result (0: a, 1: b).
 int launch_radix_sort(uint32_t* key_a, uint32_t* key_b, uint32_t* val_a, uint32_t* val_b, int64_t n_max,
                       const unsigned long long* n_dev, int end_bit, uint32_t* hist /*[passes][256]*/,
-                      uint32_t* lookback, unsigned int* tickets, cudaStream_t stream, bool hist_ready = false);
+                      uint32_t* lookback, unsigned int* tickets, cudaStream_t stream);
 bool tile_counts_path(int tiles);  // scan_emit also produces tile ranges + blend schedule (small tile grids)
 int tile_count_stride();
 void launch_depth_order(GeomState& gs, int P, cudaStream_t stream);                     // stable sort of Gaussian ids by depth bits
