@@ -70,14 +70,17 @@ int b200gs_hparams_advance(b200gs_hparams_t* hp_device, float lr_init, float lr_
 
 /* loss_out (device f64[4]): [0] += (1-l)*L1 + l*(1-SSIM), [1] L1, [2] SSIM (both means), written by the last block.
  * scratch: device f32[3*3*H*W] (the three derivative maps).  dL_dimage: device f32[3,H,W], fully written.
- * accum: device f64[4], must be zero on entry (the kernel leaves it zero on exit). */
+ * accum: device f64[b200gs_loss_accum_doubles()], must be zero on entry (the kernel leaves it zero on exit); partial
+ * sums are spread over 64 lines so that the per-block atomics do not serialise in L2. */
 int b200gs_photometric_loss(const float* image, const float* gt, int32_t width, int32_t height,
                             const b200gs_hparams_t* hp_device, float* scratch, double* accum, double* loss_out,
                             float* dL_dimage, void* stream);
 size_t b200gs_photometric_scratch_bytes(int32_t width, int32_t height);
+size_t b200gs_loss_accum_doubles(void);
 
 /* loss_out[3] = depth_weight * depth_loss is ADDED to loss_out[0]; dL_ddepth: device f32[H*W], fully written.
- * accum: device f64[16], zero on entry, left zero on exit. */
+ * accum: its own device f64[b200gs_loss_accum_doubles()], zero on entry, left zero on exit (the last few words carry
+ * the gradient coefficients from the reduction kernel to the gradient kernel). */
 int b200gs_depth_pearson_loss(const float* depth, const float* depth_mono, int32_t n,
                               const b200gs_hparams_t* hp_device, double* accum, double* loss_out,
                               float* dL_ddepth, void* stream);

@@ -63,7 +63,8 @@ class GaussianTrainer:
         H, W = int(self.cameras[0].height), int(self.cameras[0].width)
         self.H, self.W = H, W
         self.hp_dev = torch.zeros((16,), dtype=torch.float32, device=dev)
-        self.accum = torch.zeros((4 + 16,), dtype=torch.float64, device=dev)
+        self.nacc = int(lib.b200gs_loss_accum_doubles())
+        self.accum = torch.zeros((2 * self.nacc,), dtype=torch.float64, device=dev)  # photometric | depth
         self.loss = torch.zeros((4,), dtype=torch.float64, device=dev)
         self.scratch = torch.empty((lib.b200gs_photometric_scratch_bytes(W, H) // 4,), dtype=torch.float32, device=dev)
         self.iteration = 0
@@ -169,7 +170,7 @@ class GaussianTrainer:
                                           self.scratch.data_ptr(), self.accum.data_ptr(), self.loss.data_ptr(),
                                           s.cot["color"].data_ptr(), st))
         check(lib.b200gs_depth_pearson_loss(s.depth.data_ptr(), self.mono[view].data_ptr(), self.W * self.H, self.hp_dev.data_ptr(),
-                                            self.accum[4:].data_ptr(), self.loss.data_ptr(), s.cot["depth"].data_ptr(), st))
+                                            self.accum[self.nacc:].data_ptr(), self.loss.data_ptr(), s.cot["depth"].data_ptr(), st))
         s.backward()
 
     def _back(self, view):

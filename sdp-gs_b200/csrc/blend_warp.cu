@@ -407,16 +407,25 @@ __global__ void __launch_bounds__(32) blend_backward_warp_kernel(
 // B200GS_BLEND selects the blend kernels for A/B measurements: "warp" (this file), "async" (blend_async.cu),
 // "pipe" (blend_pipe.cu), "tile" (CTA per tile, blend.cu).  Optional suffixes pick per direction, e.g. B200GS_BLEND=pipe,warp = forward pipe, backward warp.
 int blend_variant(int dir) {
-	static int v[2] = {-1, -1};
-	if (v[0] < 0) {
+	static int v[2] = {-2, -2};
+	if (v[0] == -2) {
 		const char* e = getenv("B200GS_BLEND");
-		auto parse = [](const char* s, int dflt) { return (!s || !*s) ? dflt : (*s == 'a' ? 3 : (*s == 'p' ? 2 : (*s == 't' ? 1 : 0))); };
-		// defaults (measured, profiles/): forward = async list prefetch, backward = warp-autonomous register pipeline
+		auto parse = [](const char* s) { return (!s || !*s) ? -1 : (*s == 'a' ? 3 : (*s == 'p' ? 2 : (*s == 't' ? 1 : 0))); };
 		const char* c = e ? strchr(e, ',') : nullptr;
-		v[1] = c ? parse(c + 1, 0) : parse(e, 0);
-		v[0] = parse(e, 3);
+		v[1] = c ? parse(c + 1) : parse(e);
+		v[0] = parse(e);
 	}
-	return v[dir];
+	return v[dir];  // -1: not forced, pick by shape
+}
+
+// Forward default (measured, profiles/): with few units per SM slot (small images: the kernel's duration is the walk of
+// its longest lists) the cp.async list prefetch wins (64 vs 75 us at 504x378); with many waves of units (1297x840 and up)
+// occupancy wins and the register-pipelined kernel, which needs less shared memory per warp, is faster (0.50 vs 0.56 ms at
+// 1920x1080).
+int forward_variant_for(unsigned units) {
+	const int forced = blend_variant(0);
+	if (forced >= 0) return forced;
+	return units < 4u * 148u * 24u ? 3 : 0;
 }
 
 }  // namespace
@@ -435,11 +444,12 @@ void launch_blend_backward_pipe(const b200gs_view_t& v, GeomState& gs, BinningSt
 
 void launch_blend_forward(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
                           const b200gs_outputs_t& out, cudaStream_t stream) {
-	if (blend_variant(0) == 3) return launch_blend_forward_async(v, gs, bs, is, out, stream);
-	if (blend_variant(0) == 2) return launch_blend_forward_pipe(v, gs, bs, is, out, stream);
-	if (blend_variant(0) == 1) return launch_blend_forward_tile(v, gs, bs, is, out, stream);
 	const int gx = (v.width + TILE_X - 1) / TILE_X, gy = (v.height + TILE_Y - 1) / TILE_Y;
 	const unsigned units = (unsigned)(gx * gy * 8);
+	const int variant = forward_variant_for(units);
+	if (variant == 3) return launch_blend_forward_async(v, gs, bs, is, out, stream);
+	if (variant == 2) return launch_blend_forward_pipe(v, gs, bs, is, out, stream);
+	if (variant == 1) return launch_blend_forward_tile(v, gs, bs, is, out, stream);
 	if (v.extended)
 		launch_k(PDL_BLEND_FWD, blend_forward_warp_kernel<true>, dim3(units), dim3(32), stream, is.ranges, is.tile_order, bs.sorted_vals, gs.rec, v.width, v.height, gx,
 			v.background, is.final_T, is.n_contrib, out.color, out.depth, out.alpha, out.feature);

@@ -22,13 +22,15 @@ namespace {
 constexpr int LT = 16;        // tile edge
 constexpr int HALO = 5;
 constexpr int LW = LT + 2 * HALO;  // 26
+constexpr int ACC_SLOTS = 64;      // partial sums are spread over this many L2 lines: same-address f64 atomics from
+                                   // thousands of blocks serialise in L2 (ncu: 24 us for a 504x378 image before the spread)
 
 struct Window { float w[11]; };
 
 __global__ void __launch_bounds__(LT * LT) ssim_l1_forward_kernel(
 	const float* __restrict__ img, const float* __restrict__ gt, int W, int H, Window win,
 	float* __restrict__ mapA, float* __restrict__ mapB, float* __restrict__ mapC,
-	double* __restrict__ accum /*[0] sum|x-y|, [1] sum ssim, [3] block counter*/, const b200gs_hparams_t* __restrict__ hp,
+	double* __restrict__ accum /*[ACC_SLOTS][2] = {sum|x-y|, sum ssim}, then the block counter*/, const b200gs_hparams_t* __restrict__ hp,
 	double* __restrict__ loss_out)
 {
 	__shared__ float sx[LW][LW + 1], sy[LW][LW + 1];
@@ -90,24 +92,41 @@ __global__ void __launch_bounds__(LT * LT) ssim_l1_forward_kernel(
 	for (int o = 16; o > 0; o >>= 1) { l1 += __shfl_xor_sync(0xFFFFFFFFu, l1, o); ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o); }
 	if ((tid & 31) == 0) { red[0][tid >> 5] = l1; red[1][tid >> 5] = ss; }
 	__syncthreads();
+	__shared__ bool s_last;
 	if (tid == 0) {
 		double a = 0.0, b = 0.0;
 		for (int i = 0; i < LT * LT / 32; i++) { a += red[0][i]; b += red[1][i]; }
-		atomicAdd(accum, a);
-		atomicAdd(accum + 1, b);
+		const unsigned lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+		double* slot = accum + 16 * (lin % ACC_SLOTS);  // one 128-byte line per slot
+		atomicAdd(slot, a);
+		atomicAdd(slot + 1, b);
 		__threadfence();
-		unsigned long long* counter = reinterpret_cast<unsigned long long*>(accum + 3);
+		unsigned long long* counter = reinterpret_cast<unsigned long long*>(accum + 16 * ACC_SLOTS);
 		const unsigned long long total = (unsigned long long)gridDim.x * gridDim.y * gridDim.z;
-		if (atomicAdd(counter, 1ull) == total - 1) {  // last block: finish the scalars, leave the accumulators zero
-			__threadfence();
-			const double n = 3.0 * (double)W * (double)H;
-			const double L1 = __ldcg(accum) / n, S = __ldcg(accum + 1) / n;
-			const double lam = (double)hp->lambda_dssim;
-			loss_out[0] = (1.0 - lam) * L1 + lam * (1.0 - S);
-			loss_out[1] = L1;
-			loss_out[2] = S;
-			accum[0] = 0.0; accum[1] = 0.0; *counter = 0ull;
-		}
+		s_last = atomicAdd(counter, 1ull) == total - 1;
+	}
+	__syncthreads();
+	if (!s_last) return;
+	// last block: the 64 slots are gathered by 64 threads (one L2 round trip, not 64), the accumulators are left zero
+	__threadfence();
+	double sa = 0.0, sb = 0.0;
+	if (tid < ACC_SLOTS) {
+		sa = __ldcg(accum + 16 * tid); sb = __ldcg(accum + 16 * tid + 1);
+		accum[16 * tid] = 0.0; accum[16 * tid + 1] = 0.0;
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) { sa += __shfl_xor_sync(0xFFFFFFFFu, sa, o); sb += __shfl_xor_sync(0xFFFFFFFFu, sb, o); }
+	if ((tid & 31) == 0) { red[0][tid >> 5] = sa; red[1][tid >> 5] = sb; }
+	__syncthreads();
+	if (tid == 0) {
+		sa = red[0][0] + red[0][1]; sb = red[1][0] + red[1][1];  // ACC_SLOTS = 64 = two warps
+		const double n = 3.0 * (double)W * (double)H;
+		const double L1 = sa / n, S = sb / n;
+		const double lam = (double)hp->lambda_dssim;
+		loss_out[0] = (1.0 - lam) * L1 + lam * (1.0 - S);
+		loss_out[1] = L1;
+		loss_out[2] = S;
+		*reinterpret_cast<unsigned long long*>(accum + 16 * ACC_SLOTS) = 0ull;
 	}
 }
 
@@ -168,7 +187,8 @@ __global__ void __launch_bounds__(LT * LT) ssim_l1_backward_kernel(
 // r = Sxy / sqrt(Sxx Syy) over centred sums; loss = w * min(1 - r1, 1 - r2);
 // dL/dy_i = w * ( -(x_i - mx) / sqrt(Sxx Syy) + r (y_i - my) / Syy ) for the selected branch = A x_i + B y_i + C0.
 __global__ void __launch_bounds__(256) pearson_reduce_kernel(
-	const float* __restrict__ depth, const float* __restrict__ mono, int n, double* __restrict__ accum /*[16]*/,
+	const float* __restrict__ depth, const float* __restrict__ mono, int n,
+	double* __restrict__ accum /*[ACC_SLOTS][16] partial sums (8 used), then counter, then 4 coefficients*/,
 	const b200gs_hparams_t* __restrict__ hp, double* __restrict__ loss_out)
 {
 	__shared__ double red[8][8];
@@ -195,17 +215,38 @@ __global__ void __launch_bounds__(256) pearson_reduce_kernel(
 	if (threadIdx.x < 8) {
 		double t = 0.0;
 		for (int w = 0; w < 8; w++) t += red[threadIdx.x][w];
-		atomicAdd(accum + threadIdx.x, t);
+		atomicAdd(accum + 16 * (blockIdx.x % ACC_SLOTS) + threadIdx.x, t);
 	}
 	__syncthreads();
+	__shared__ bool s_last;
 	if (threadIdx.x == 0) {
 		__threadfence();
-		unsigned long long* counter = reinterpret_cast<unsigned long long*>(accum + 8);
-		if (atomicAdd(counter, 1ull) == (unsigned long long)gridDim.x - 1) {
-			__threadfence();
+		unsigned long long* counter = reinterpret_cast<unsigned long long*>(accum + 16 * ACC_SLOTS);
+		s_last = atomicAdd(counter, 1ull) == (unsigned long long)gridDim.x - 1;
+	}
+	__syncthreads();
+	if (!s_last) return;
+	__threadfence();
+	{   // last block: thread (slot, k) gathers one partial sum; 8 x 64 values reduced over the slots through shared memory
+		__shared__ double part[ACC_SLOTS][8];
+		for (int i = threadIdx.x; i < ACC_SLOTS * 8; i += blockDim.x) {
+			const int sl = i >> 3, k = i & 7;
+			part[sl][k] = __ldcg(accum + 16 * sl + k);
+			accum[16 * sl + k] = 0.0;
+		}
+		__syncthreads();
+		if (threadIdx.x < 8) {
+			double t = 0.0;
+			for (int sl = 0; sl < ACC_SLOTS; sl++) t += part[sl][threadIdx.x];
+			red[threadIdx.x][0] = t;
+		}
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) {
+		{
 			double t[8];
-			for (int k = 0; k < 8; k++) { t[k] = __ldcg(accum + k); accum[k] = 0.0; }
-			*counter = 0ull;
+			for (int k = 0; k < 8; k++) t[k] = red[k][0];
+			*reinterpret_cast<unsigned long long*>(accum + 16 * ACC_SLOTS) = 0ull;
 			const double N = (double)n;
 			const double my = t[0] / N, Syy = t[1] - t[0] * t[0] / N;
 			const double m1 = t[2] / N, S11 = t[3] - t[2] * t[2] / N, S1y = t[4] - t[2] * t[0] / N;
@@ -216,10 +257,11 @@ __global__ void __launch_bounds__(256) pearson_reduce_kernel(
 			const double w = (double)hp->depth_weight;
 			const bool first = (1.0 - r1) <= (1.0 - r2);  // python min(a, b) returns a on ties
 			const double r = first ? r1 : r2, D = first ? D1 : D2, mx = first ? m1 : m2;
-			accum[10] = -w / D;                               // A
-			accum[11] = w * r / Syy;                          // B
-			accum[12] = w * (mx / D - r * my / Syy);          // C0
-			accum[13] = first ? 0.0 : 1.0;                    // which x
+			double* coef = accum + 16 * ACC_SLOTS + 2;
+			coef[0] = -w / D;                               // A
+			coef[1] = w * r / Syy;                          // B
+			coef[2] = w * (mx / D - r * my / Syy);          // C0
+			coef[3] = first ? 0.0 : 1.0;                    // which x
 			const double dl = w * (1.0 - r);
 			loss_out[3] = dl;
 			loss_out[0] += dl;
@@ -228,7 +270,7 @@ __global__ void __launch_bounds__(256) pearson_reduce_kernel(
 }
 
 __global__ void __launch_bounds__(256) pearson_grad_kernel(const float* __restrict__ depth, const float* __restrict__ mono, int n,
-                                                           const double* coef /*accum + 10*/, float* __restrict__ dL_ddepth)
+                                                           const double* coef, float* __restrict__ dL_ddepth)
 {
 	pdl_trigger();
 	pdl_wait();
@@ -366,6 +408,7 @@ Window make_window() {
 extern "C" {
 
 size_t b200gs_photometric_scratch_bytes(int32_t width, int32_t height) { return (size_t)9 * width * height * sizeof(float); }
+size_t b200gs_loss_accum_doubles(void) { return (size_t)16 * ACC_SLOTS + 8; }
 
 int b200gs_photometric_loss(const float* image, const float* gt, int32_t width, int32_t height,
                             const b200gs_hparams_t* hp, float* scratch, double* accum, double* loss_out,
@@ -394,7 +437,7 @@ int b200gs_depth_pearson_loss(const float* depth, const float* depth_mono, int32
 	cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
 	const unsigned grid = (unsigned)min((n + 255) / 256, 148 * 4);
 	launch_k(PDL_TRAIN, pearson_reduce_kernel, dim3(grid), dim3(256), stream, depth, depth_mono, (int)n, accum, hp, loss_out);
-	launch_k(PDL_TRAIN, pearson_grad_kernel, dim3(grid), dim3(256), stream, depth, depth_mono, (int)n, (const double*)(accum + 10), dL_ddepth);
+	launch_k(PDL_TRAIN, pearson_grad_kernel, dim3(grid), dim3(256), stream, depth, depth_mono, (int)n, (const double*)(accum + 16 * ACC_SLOTS + 2), dL_ddepth);
 	count_launch(2);
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return train_fail(B200GS_E_CUDA, cudaGetErrorString(e));

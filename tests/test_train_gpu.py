@@ -53,7 +53,8 @@ def test_photometric_and_depth_loss_match_torch(W, H):
     depth = (torch.rand((1, H, W), generator=g) * 5 + 1).to(dev)
     mono = (0.5 * depth.cpu() + torch.rand((1, H, W), generator=g) * 2 + 0.5).to(dev)
     hp, vals = _hp_block(dev)
-    accum = torch.zeros(20, dtype=torch.float64, device=dev)
+    nacc = int(lib.b200gs_loss_accum_doubles())
+    accum = torch.zeros(2 * nacc, dtype=torch.float64, device=dev)
     loss = torch.zeros(4, dtype=torch.float64, device=dev)
     scratch = torch.empty(lib.b200gs_photometric_scratch_bytes(W, H) // 4, dtype=torch.float32, device=dev)
     d_img = torch.full((3, H, W), float("nan"), device=dev)
@@ -62,10 +63,10 @@ def test_photometric_and_depth_loss_match_torch(W, H):
     for _ in range(2):  # twice: the accumulators must be left clean
         check(lib.b200gs_photometric_loss(img.data_ptr(), gt.data_ptr(), W, H, hp.data_ptr(), scratch.data_ptr(), accum.data_ptr(),
                                           loss.data_ptr(), d_img.data_ptr(), st))
-        check(lib.b200gs_depth_pearson_loss(depth.data_ptr(), mono.data_ptr(), W * H, hp.data_ptr(), accum[4:].data_ptr(),
+        check(lib.b200gs_depth_pearson_loss(depth.data_ptr(), mono.data_ptr(), W * H, hp.data_ptr(), accum[nacc:].data_ptr(),
                                             loss.data_ptr(), d_depth.data_ptr(), st))
     torch.cuda.synchronize()
-    assert float(accum[:10].abs().sum()) == 0.0
+    assert float(accum[:nacc].abs().sum()) == 0.0 and float(accum[nacc:2 * nacc - 8].abs().sum()) == 0.0
 
     ti, td = img.clone().requires_grad_(True), depth.clone().requires_grad_(True)
     total, l1, s, dl = tt.total_loss(ti, gt, td, mono, vals["lambda_dssim"], vals["depth_weight"])
