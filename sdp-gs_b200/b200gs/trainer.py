@@ -310,6 +310,38 @@ class GaussianTrainer:
         self.m["opacity"].zero_(); self.v["opacity"].zero_()
         self._refresh_activations()
 
+    # ------------------------------------------------------------------ persistence
+    def capture_state(self):
+        """What GaussianModel.capture() keeps (scene/gaussian_model.py:67-102), in this trainer's layout: raw parameters, Adam
+        moments (the optimizer state dict), densification statistics and the iteration count -- CPU tensors, picklable."""
+        c = lambda t: t.detach().cpu().clone()
+        return dict(iteration=self.iteration, hparams=dict(self.hp), raw={k: c(v) for k, v in self.raw.items()},
+                    exp_avg={k: c(v) for k, v in self.m.items()}, exp_avg_sq={k: c(v) for k, v in self.v.items()},
+                    xyz_gradient_accum=c(self.bucket.segment("xyz_gradient_accum")), denom=c(self.bucket.segment("denom")),
+                    max_radii2D=c(self.bucket.max_radii2D))
+
+    def restore(self, state, recapture=True):
+        """Inverse of capture_state (GaussianModel.restore, scene/gaussian_model.py:104-143)."""
+        to = lambda t: t.to(self.dev, dtype=torch.float32)
+        self.hp.update(state.get("hparams", {}))
+        self._allocate({k: to(v) for k, v in state["raw"].items()}, {k: to(v) for k, v in state["exp_avg"].items()},
+                       {k: to(v) for k, v in state["exp_avg_sq"].items()})
+        self.bucket.segment("xyz_gradient_accum").copy_(to(state["xyz_gradient_accum"]))
+        self.bucket.segment("denom").copy_(to(state["denom"]))
+        self.bucket.max_radii2D.copy_(state["max_radii2D"].to(self.dev))
+        self.iteration = int(state["iteration"])
+        self.set_hparams(step=self.iteration + 1)
+        self._refresh_activations()
+        if recapture:
+            self.capture()
+
+    def save_ply(self, path):
+        """Point cloud in the reference's PLY layout (scene/gaussian_model.py:303-325) through b200gs.ply_io."""
+        from . import ply_io
+        n = lambda t: t.detach().cpu().numpy()
+        ply_io.save_ply(path, xyz=n(self.raw["xyz"]), shs=n(self.raw["shs"]).reshape(self.P, 16, 3), opacity=n(self.raw["opacity"]),
+                        scaling=n(self.raw["scaling"]), rotation=n(self.raw["rotation"]), feature=n(self.raw["feature"]))
+
     def loss_values(self):
         """(total, L1, SSIM, weighted depth loss) of the last step."""
         t = self.loss.cpu().numpy()
