@@ -66,3 +66,24 @@ def test_stress_train_shape_forward_backward():
     for k in ("means3D", "opacities", "shs"):
         assert rel_err(p2["grads"][k], -0.5 * np.asarray(p["grads"][k])) <= 1e-4, k
     np.testing.assert_array_equal(bits(p2["color"]), bits(p["color"]))
+
+
+def test_dtu_scan_shape_forward_backward():
+    """configs[2]: ~300k Gaussians at 400x300 (25x19 = 475 tiles, 9-bit tile ids) with the rendered-depth output that feeds
+    depthfusion.py: every integer stage bit-exact against the CPU oracle, maps within 1e-4, gradients within 1e-3."""
+    import torch
+    assert torch.cuda.is_available()
+    inp = _inputs("dtu_scan_3view", 2, extended=True)
+    cot = helpers.case_cotangents(inp, seed=5)
+    p = run_product(inp, True, cot)
+    _check_sorted(p)
+    o = run_oracle(inp, True, cot)
+    assert p["num_rendered"] == o["num_rendered"]
+    for k in ("radii", "tiles_touched", "point_list", "point_list_keys", "ranges"):
+        np.testing.assert_array_equal(p[k], o[k], err_msg=k)
+    np.testing.assert_array_equal(bits(p["depths"]), bits(o["depths"]))
+    assert (p["n_contrib"] != o["n_contrib"]).mean() <= 1e-3
+    for k in ("color", "depth", "alpha", "feature"):
+        assert np.abs(p[k] - o[k]).max() <= 1e-4, k
+    for k in ("means3D", "opacities", "scales", "rotations", "shs", "features"):
+        assert rel_err(p["grads"][k], o["grads"][k]) <= 1e-3, k
