@@ -452,7 +452,7 @@ def train_reference(args, wl, binning_bytes, flush):
     second call with colors_precomp = (z, 1, f0), bg 0 -- the vendored kernel has no depth output), torch activations,
     torch losses (utils/loss_utils.py restated in oracle/train_torch.py) and torch.optim.Adam with its 7 groups."""
     from oracle import ref_cuda, train_torch as tt
-    from b200gs.trainer import DEFAULTS, expon_lr
+    from b200gs.schedule import DEFAULTS, expon_lr  # pure Python: this arm must never map libb200gs.so
     dev = wl.dev
     P = wl.scene.P
     gts, monos = train_targets(wl)

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200gs.so")
+# B200GS_LIB: developer knob for A/B builds of the same library (tools/build_variants.sh); never a different backend
+LIB_PATH = os.environ.get("B200GS_LIB") or os.path.join(_HERE, "libb200gs.so")
 
 c_float_p = C.c_void_p  # device pointers are passed as integers
 

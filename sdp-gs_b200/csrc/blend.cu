@@ -1,294 +1,603 @@
-// b200gs -- per-tile alpha blending: forward (K6) and backward (K7).
+// b200gs -- alpha blending, forward (K6) and backward (K7).
 //
-// Semantics: DGR/cuda_rasterizer/forward.cu:261-374 and backward.cu:399-557, generalised from 3
-// colour channels to the 8 blended channels SDP-GS reads, [r,g,b | z | 1 | f0,f1,f2] (SURVEY.md
-// Appendix D; background only under r,g,b).  One CTA per 16x16 tile as in the reference (tile
-// ranges are part of the bit-exact contract), but:
-//   * a warp owns a compact 8x4 pixel block, and before touching a batch each lane tests one
-//     Gaussian's 1/255-alpha ellipse against the warp's block (exact minimum of the conic's
-//     quadratic form over the block's visible edges, with a rounding margin).  Only Gaussians
-//     that can reach alpha >= 1/255 somewhere in the block are evaluated per pixel.  The test is
-//     conservative, so every (pixel, Gaussian) pair the reference blends is blended here with
-//     the same arithmetic sequence (power = fma(q, -0.5, -(dy*(dx*b))), CUDA expf, ...);
-//   * a batch's records (64 B per Gaussian: position, conic, opacity, colour, depth, feature)
-//     are staged in shared memory once, so the inner loop never touches global memory (the
-//     reference fetches colours from global per blended pair, forward.cu:355);
-//   * the backward replaces the reference's 9 global float atomics per blended pair
-//     (backward.cu:523,545-554) with a warp butterfly reduce-scatter, shared-memory accumulation
-//     per batch and one 16-byte vector reduction (red.global.add.v4.f32) per (tile, Gaussian,
-//     4 values).
+// Semantics: DGR/cuda_rasterizer/forward.cu:261-374 and backward.cu:399-557, generalised from 3 colour
+// channels to the 8 blended channels SDP-GS reads, [r,g,b | z | 1 | f0,f1,f2] (SURVEY.md Appendix D;
+// background only under r,g,b).  Per-pair arithmetic is the reference's, operation for operation (power =
+// fma(q, -0.5, -(dy*(dx*b))), CUDA expf, fma(T, alpha*c, C)), so the image is bit-identical; the decomposition
+// is not the reference's:
+//   * unit of work = one warp = one 8x4 pixel block of a 16x16 tile.  Warps are autonomous (no CTA barrier
+//     anywhere): a persistent grid of 4-warp CTAs draws units from a global ticket, longest tile list first
+//     (order built by the binning stage), fewer warps than units, so SMs that drew light units keep drawing;
+//   * a round = 32 consecutive entries of the tile's sorted list, one per lane.  Ids are loaded three rounds
+//     ahead, the 32-byte geometry half of the splat record two rounds ahead (registers), the lane then runs the
+//     conservative ellipse-vs-block cull (blend_common.cuh) and only survivors (39 % on the LLFF shape) are
+//     appended, in list order, to a 64-slot ring in the warp's shared memory; their payload half (colour, depth,
+//     feature) is fetched by cp.async straight into the ring, up to K_INFLIGHT rounds of copies in flight;
+//   * per-pixel work runs on dense, 16-aligned batches of survivors read from shared memory as broadcasts with
+//     immediate offsets; the loops carry no index arithmetic, bounds checks or per-survivor bookkeeping loads
+//     (ncu, round 2: the kernels are issue bound -- 76 % / 65 % issue-slot utilisation -- on exactly these loops;
+//     trimming them from 71 / 125 to ~50 / ~85 warp instructions per survivor is what moved the time);
+//   * backward: phase 1 (lane = pixel) replays the recurrence back to front and leaves two weights per
+//     (pixel, Gaussian) pair in shared memory; phase 2 (lane = (half, Gaussian)) turns them into the 13
+//     per-Gaussian sums -- six pixel moments of wg = G*dL/dG (-> dL/dmean2D, dL/dconic, dL/dopacity) on the
+//     lower half-warp, seven channel sums of wc = alpha*T on the upper one, the same instruction stream for
+//     both: sum_p w[p] * basis[p][0..6] with a per-warp basis table.  Two red.global.add.v4.f32 per lane
+//     replace the reference's 9 float atomics per blended pair (backward.cu:523,545-554).
+#include <cstddef>
+#include <cstdio>
+#include <cstdlib>
 #include "common.cuh"
 #include "blend_common.cuh"
 
 namespace {
 
+// tuning constants (overridable with -D for A/B builds, tools/build_variants.sh)
+#ifndef B200GS_BLEND_WARPS
+#define B200GS_BLEND_WARPS 4
+#endif
+#ifndef B200GS_K_INFLIGHT
+#define B200GS_K_INFLIGHT 2
+#endif
+#ifndef B200GS_FWD_CTAS
+#define B200GS_FWD_CTAS 0  // CTAs per SM of the persistent forward grid (0: as many as fit)
+#endif
+#ifndef B200GS_BWD_CTAS
+#define B200GS_BWD_CTAS 0
+#endif
+constexpr int BLEND_WARPS = B200GS_BLEND_WARPS;  // warps per CTA (each with a private shared-memory slice)
+constexpr int RING = 64;                         // survivor slots per warp
+constexpr int K_INFLIGHT = B200GS_K_INFLIGHT;    // commit groups (= rounds) of payload copies allowed in flight
+constexpr int BATCH = 16;                        // survivors per batch; ring positions of a batch never wrap
+constexpr int WSTRIDE = BATCH + 1;               // row stride of the pair-weight matrices (odd: conflict-free in both phases)
+#define NOID 0xFFFFFFFFu
+
+__device__ __forceinline__ uint32_t sptr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sptr(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct Unit {
+	unsigned px, py;
+	bool inside;
+	float pxf, pyf;
+	PixelBlock pb;
+	uint2 range;
+};
+
+__device__ __forceinline__ Unit make_unit(uint32_t unit, const uint32_t* order, const uint2* ranges, int W, int H, int grid_x) {
+	Unit u;
+	const unsigned lane = threadIdx.x & 31;
+	const uint32_t tile = __ldcg(order + (unit >> 3));
+	const unsigned sub = unit & 7;
+	const unsigned tx = tile % grid_x, ty = tile / grid_x;
+	const unsigned bx = tx * TILE_X + (sub & 1) * 8, by = ty * TILE_Y + (sub >> 1) * 4;
+	u.px = bx + (lane & 7);
+	u.py = by + (lane >> 3);
+	u.inside = u.px < (unsigned)W && u.py < (unsigned)H;
+	u.pxf = (float)u.px;
+	u.pyf = (float)u.py;
+	u.pb.X0 = (float)bx; u.pb.X1 = u.pb.X0 + 7.f;
+	u.pb.Y0 = (float)by; u.pb.Y1 = u.pb.Y0 + 3.f;
+	u.range = __ldcg(ranges + tile);
+	return u;
+}
+
+// Per-warp shared memory.
 template <bool EXT>
-__global__ void __launch_bounds__(TILE_PIX) blend_forward_kernel(
-	const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const float4* __restrict__ rec, int W, int H,
+struct FwdSmem {
+	float4 g0[RING], g1[RING], g2[RING];
+	float4 g3[EXT ? RING : 1];
+	uint32_t pos[RING];  // 1-based position of the survivor in its tile's list
+};
+template <bool EXT>
+struct BwdSmem {
+	float4 g0[RING], g1[RING], g2[RING];
+	float4 g3[EXT ? RING : 1];
+	uint32_t pos[RING];
+	uint32_t id[RING];
+	float4 basis[32][2][2];          // [pixel][half]: {1, cx, cy, cx^2 | cx*cy, cy^2, 0, 0} / {dL/d(r,g,b,z) | dL/d(f0,f1,f2), 0}
+	float w[2][32 * WSTRIDE + 16];   // [0]: wg = G*dL/dG, [1]: wc = alpha*T; the +16 puts the two planes 16 banks apart
+};
+
+// The list walk shared by both directions.  Walk entry i is list position pos(i): forward i, backward top - i
+// (deepest contributor first).  Lane l handles entry 32 r + l of round r.
+template <bool FWD>
+struct Walk {
+	const uint32_t* list;   // point_list + range.x
+	const float4* rec;
+	int n, top;
+	unsigned lane;
+	__device__ __forceinline__ int pos(int i) const { return FWD ? i : top - i; }
+	__device__ __forceinline__ uint32_t load_id(int r) const {
+		const int i = 32 * r + (int)lane;
+		return i < n ? __ldcg(list + pos(i)) : NOID;
+	}
+	__device__ __forceinline__ void load_geo(uint32_t id, float4& g0, float4& g1) const {
+		if (id != NOID) { const float4* p = rec + 4 * (size_t)id; g0 = __ldca(p); g1 = __ldca(p + 1); }
+	}
+	// cull round r; survivors go to ring slots head.. in walk order, their payload copies are issued
+	template <bool EXT, bool WITH_ID, typename S>
+	__device__ __forceinline__ int stage(S& s, int r, uint32_t id, const float4 g0, const float4 g1, const PixelBlock& pb, int head) const {
+		const bool keep = id != NOID && !cull_block(g0, g1, pb);
+		const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+		if (m == 0u) return 0;
+		if (keep) {
+			const int slot = (head + __popc(m & ((1u << lane) - 1u))) & (RING - 1);
+			const float4* src = rec + 4 * (size_t)id + 2;
+			cp_async16(&s.g2[slot], src);
+			if (EXT) cp_async16(&s.g3[slot], src + 1);
+			s.g0[slot] = g0;
+			s.g1[slot] = g1;
+			s.pos[slot] = (uint32_t)(pos(32 * r + (int)lane) + 1);
+			if (WITH_ID) s.pos[RING + slot] = id;  // BwdSmem::id follows pos
+		}
+		return __popc(m);
+	}
+};
+static_assert(offsetof(BwdSmem<true>, id) == offsetof(BwdSmem<true>, pos) + RING * 4, "id follows pos");
+static_assert(offsetof(BwdSmem<false>, id) == offsetof(BwdSmem<false>, pos) + RING * 4, "id follows pos");
+
+// Persistent unit loop: lane 0 draws the next unit from the ticket; the last warp to run dry re-arms both
+// counters, so the kernel can be launched again on the same workspace without a memset.
+struct Ticket {
+	unsigned int* ticket;
+	unsigned int* exits;
+	__device__ __forceinline__ uint32_t next(unsigned lane) const {
+		uint32_t u = 0;
+		if (lane == 0) u = atomicAdd(ticket, 1u);
+		return __shfl_sync(0xFFFFFFFFu, u, 0);
+	}
+	__device__ __forceinline__ void leave(unsigned lane, unsigned total_warps) const {
+		if (lane == 0) {
+			__threadfence();
+			if (atomicAdd(exits, 1u) == total_warps - 1u) { atomicExch(ticket, 0u); atomicExch(exits, 0u); }
+		}
+	}
+};
+
+template <bool EXT>
+__global__ void __launch_bounds__(BLEND_WARPS * 32) blend_forward_kernel(
+	const uint2* ranges, const uint32_t* order, const uint32_t* point_list, const float4* rec,
+	int W, int H, int grid_x, uint32_t units, unsigned int* ticket, unsigned int* exits,
 	const float* __restrict__ bg, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
 	float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_alpha, float* __restrict__ out_feat)
 {
-	__shared__ float4 s_g0[TILE_PIX], s_g1[TILE_PIX], s_g2[TILE_PIX];
-	__shared__ float4 s_g3[EXT ? TILE_PIX : 1];
+	constexpr int NC = EXT ? 8 : 3;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	FwdSmem<EXT>& S = reinterpret_cast<FwdSmem<EXT>*>(smem_raw)[threadIdx.x >> 5];
+	const unsigned lane = threadIdx.x & 31;
+	pdl_trigger();
+	pdl_wait();
+	const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
+	const Ticket tk{ticket, exits};
 
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int bx = (warp & 1) * 8, by = (warp >> 1) * 4;
-	const unsigned px = blockIdx.x * TILE_X + bx + (lane & 7), py = blockIdx.y * TILE_Y + by + (lane >> 3);
-	const bool inside = px < (unsigned)W && py < (unsigned)H;
-	const float pxf = (float)px, pyf = (float)py;
-	PixelBlock pb;
-	pb.X0 = (float)(blockIdx.x * TILE_X + bx); pb.X1 = pb.X0 + 7.f;
-	pb.Y0 = (float)(blockIdx.y * TILE_Y + by); pb.Y1 = pb.Y0 + 3.f;
+	for (uint32_t unit = tk.next(lane); unit < units; unit = tk.next(lane)) {
+		const Unit u = make_unit(unit, order, ranges, W, H, grid_x);
+		Walk<true> wk;
+		wk.list = point_list + u.range.x; wk.rec = rec; wk.n = (int)(u.range.y - u.range.x); wk.top = 0; wk.lane = lane;
+		const int R = (wk.n + 31) >> 5;
 
-	const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
-	const int n = (int)(range.y - range.x);
-
-	bool done = !inside;
-	float T = 1.0f;
-	uint32_t last_contributor = 0;
-	float C[EXT ? 8 : 3];
+		bool done = !u.inside;
+		float T = 1.0f;
+		int lc = -1;                    // ring-absolute index of the last survivor blended into this pixel
+		uint32_t last_contributor = 0;  // ... and its 1-based list position (looked up once per batch)
+		float C[NC];
 #pragma unroll
-	for (int ch = 0; ch < (EXT ? 8 : 3); ch++) C[ch] = 0.f;
+		for (int ch = 0; ch < NC; ch++) C[ch] = 0.f;
 
-	for (int base = 0; base < n; base += TILE_PIX) {
-		if (__syncthreads_and(done)) break;
-		const int cnt = min(TILE_PIX, n - base);
-		if (tid < cnt) {
-			const uint32_t id = point_list[range.x + base + tid];
-			const float4* r = rec + 4 * (size_t)id;
-			s_g0[tid] = __ldg(r); s_g1[tid] = __ldg(r + 1); s_g2[tid] = __ldg(r + 2);
-			if (EXT) s_g3[tid] = __ldg(r + 3);
-		}
-		__syncthreads();
-		if (__all_sync(0xFFFFFFFFu, done)) continue;
-		for (int m = 0; m * 32 < cnt; m++) {
-			const int jj = m * 32 + lane;
-			bool keep = false;
-			if (jj < cnt) keep = !cull_block(s_g0[jj], s_g1[jj], pb);
-			unsigned mask = __ballot_sync(0xFFFFFFFFu, keep);
-			while (mask) {
-				const int j = m * 32 + (__ffs(mask) - 1);
-				mask &= mask - 1;
-				if (done) continue;
-				const float4 g0 = s_g0[j];
-				const float4 g1 = s_g1[j];
-				const float dx = __fsub_rn(g0.x, pxf), dy = __fsub_rn(g0.y, pyf);
-				const float power = pair_power(dx, dy, g0.z, g0.w, g1.x);
-				if (power > 0.0f) continue;
-				const float alpha = fminf(0.99f, __fmul_rn(g1.y, expf(power)));
-				if (alpha < 1.0f / 255.0f) continue;
+		// Blend four staged survivors at ring slots base..base+3 (base % 4 == 0, front to back).  First the four alphas
+		// (independent), then the recurrence, branch-free: a pair that is skipped or comes after the pixel is saturated
+		// accumulates with weight 0 (exact for finite payloads).  T >= 1e-4 holds while the pixel is live, so a skipped
+		// pair (alpha = 0, test_T == T) can never trip the saturation test.
+		auto group4 = [&](int base, int abs0) {
+			float al[4];
+			float4 cc[4], ff[4];
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				const float4 a = S.g0[base + k];
+				const float4 b = S.g1[base + k];
+				cc[k] = S.g2[base + k];
+				if (EXT) ff[k] = S.g3[base + k];
+				const float dx = __fsub_rn(a.x, u.pxf), dy = __fsub_rn(a.y, u.pyf);
+				const float power = pair_power(dx, dy, a.z, a.w, b.x);
+				const float alpha = fminf(0.99f, __fmul_rn(b.y, expf(power)));
+				al[k] = (power > 0.0f || alpha < 1.0f / 255.0f) ? 0.f : alpha;  // 0 <=> skipped pair (forward.cu:336-345)
+			}
+			int lc_rel = -1;
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				const float alpha = al[k];
 				const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-				if (test_T < 0.0001f) { done = true; continue; }
-				const float4 g2 = s_g2[j];
-				C[0] = __fmaf_rn(T, __fmul_rn(alpha, g2.x), C[0]);
-				C[1] = __fmaf_rn(T, __fmul_rn(alpha, g2.y), C[1]);
-				C[2] = __fmaf_rn(T, __fmul_rn(alpha, g2.z), C[2]);
+				const bool pdone = done || test_T < 0.0001f;
+				const float Tb = pdone ? 0.f : T;
+				// rgb: the reference's exact sequence fma(T, alpha*c, C) (forward.cu:355), images are bit-identical
+				C[0] = __fmaf_rn(Tb, __fmul_rn(alpha, cc[k].x), C[0]);
+				C[1] = __fmaf_rn(Tb, __fmul_rn(alpha, cc[k].y), C[1]);
+				C[2] = __fmaf_rn(Tb, __fmul_rn(alpha, cc[k].z), C[2]);
 				if (EXT) {
-					const float4 g3 = s_g3[j];
-					C[3] = __fmaf_rn(T, __fmul_rn(alpha, g2.w), C[3]);
-					C[4] = __fmaf_rn(T, alpha, C[4]);
-					C[5] = __fmaf_rn(T, __fmul_rn(alpha, g3.x), C[5]);
-					C[6] = __fmaf_rn(T, __fmul_rn(alpha, g3.y), C[6]);
-					C[7] = __fmaf_rn(T, __fmul_rn(alpha, g3.z), C[7]);
+					const float wt = __fmul_rn(alpha, Tb);
+					C[3] = __fmaf_rn(wt, cc[k].w, C[3]);
+					C[4] = __fadd_rn(C[4], wt);
+					C[5] = __fmaf_rn(wt, ff[k].x, C[5]);
+					C[6] = __fmaf_rn(wt, ff[k].y, C[6]);
+					C[7] = __fmaf_rn(wt, ff[k].z, C[7]);
 				}
-				T = test_T;
-				last_contributor = (uint32_t)(base + j + 1);
+				lc_rel = (!pdone && alpha != 0.f) ? k : lc_rel;
+				T = pdone ? T : test_T;
+				done = pdone;
+			}
+			lc = lc_rel >= 0 ? abs0 + lc_rel : lc;
+		};
+		// groups [tail, tail + 4*ngroups): tail is a multiple of 16 (or of 4 in the final flush), so a group never wraps
+		auto process = [&](int tail, int ngroups) {
+			const int base0 = tail & (RING - 1);
+			for (int j = 0; j < ngroups; j++) group4(base0 + 4 * j, tail + 4 * j);
+			if (lc >= tail) last_contributor = S.pos[lc & (RING - 1)];  // before the slot can be recycled
+		};
+
+		if (R > 0) {
+			float4 ga0, ga1, gb0, gb1;
+			ga0 = ga1 = gb0 = gb1 = make_float4(0.f, 0.f, 0.f, 0.f);
+			uint32_t ida = wk.load_id(0), idb = wk.load_id(1), idc = wk.load_id(2);
+			wk.load_geo(ida, ga0, ga1);
+			wk.load_geo(idb, gb0, gb1);
+			int head = 0, tail = 0;
+			int hist[K_INFLIGHT + 1];  // hist[j] = head after round r-1-j: what has landed is hist[K_INFLIGHT]
+#pragma unroll
+			for (int j = 0; j <= K_INFLIGHT; j++) hist[j] = 0;
+			bool all_done = false;
+			for (int r = 0; r < R; r++) {
+				const uint32_t idd = wk.load_id(r + 3);            // ids, round r+3
+				float4 gc0 = make_float4(0.f, 0.f, 0.f, 0.f), gc1 = gc0;
+				wk.load_geo(idc, gc0, gc1);                        // geometry, round r+2
+				cp_wait<K_INFLIGHT>();  // every group but the latest K has landed: survivors of rounds <= r-1-K are complete
+				if (hist[K_INFLIGHT] - tail >= BATCH || head - tail > RING - 32) {
+					if (head - tail > RING - 32) { cp_wait<0>(); hist[K_INFLIGHT] = head; }  // a dense stretch: make room for a full round
+					__syncwarp();
+					do { process(tail, BATCH / 4); tail += BATCH; } while (hist[K_INFLIGHT] - tail >= BATCH);
+					__syncwarp();
+					all_done = __all_sync(0xFFFFFFFFu, done);
+					if (all_done) break;
+				}
+				head += wk.template stage<EXT, false>(S, r, ida, ga0, ga1, u.pb, head);
+				cp_commit();
+#pragma unroll
+				for (int j = K_INFLIGHT; j > 0; j--) hist[j] = hist[j - 1];
+				hist[0] = head;
+				ga0 = gb0; ga1 = gb1; gb0 = gc0; gb1 = gc1;
+				ida = idb; idb = idc; idc = idd;
+			}
+			cp_wait<0>();
+			if (!all_done && head > tail) {
+				// final flush: pad with inert survivors (opacity 0, finite payload) up to a multiple of 4
+				const int pad = (tail - head) & 3;
+				if ((int)lane < pad) {
+					const int slot = (head + (int)lane) & (RING - 1);
+					const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+					S.g0[slot] = z; S.g1[slot] = z; S.g2[slot] = z;
+					if (EXT) S.g3[slot] = z;
+				}
+				head += pad;
+				__syncwarp();
+				while (head > tail) {
+					const int g = min(BATCH, head - tail) / 4;
+					process(tail, g);
+					tail += 4 * g;
+					if (__all_sync(0xFFFFFFFFu, done)) break;
+				}
+			}
+			__syncwarp();  // the ring is reused by the next unit
+		}
+		if (u.inside) {
+			const size_t pix = (size_t)u.py * W + u.px, HW = (size_t)H * W;
+			final_T[pix] = T;
+			n_contrib[pix] = last_contributor;
+			out_color[pix] = __fmaf_rn(bg0, T, C[0]);
+			out_color[HW + pix] = __fmaf_rn(bg1, T, C[1]);
+			out_color[2 * HW + pix] = __fmaf_rn(bg2, T, C[2]);
+			if (EXT) {
+				out_depth[pix] = C[3];
+				out_alpha[pix] = C[4];
+				out_feat[pix] = C[5];
+				out_feat[HW + pix] = C[6];
+				out_feat[2 * HW + pix] = C[7];
 			}
 		}
 	}
-	if (inside) {
-		const size_t pix = (size_t)py * W + px, HW = (size_t)H * W;
-		final_T[pix] = T;
-		n_contrib[pix] = last_contributor;
-		out_color[pix] = __fmaf_rn(__ldg(bg), T, C[0]);
-		out_color[HW + pix] = __fmaf_rn(__ldg(bg + 1), T, C[1]);
-		out_color[2 * HW + pix] = __fmaf_rn(__ldg(bg + 2), T, C[2]);
-		if (EXT) {
-			out_depth[pix] = C[3];
-			out_alpha[pix] = C[4];
-			out_feat[pix] = C[5];
-			out_feat[HW + pix] = C[6];
-			out_feat[2 * HW + pix] = C[7];
-		}
-	}
+	tk.leave(lane, gridDim.x * BLEND_WARPS);
 }
 
 template <bool EXT>
-__global__ void __launch_bounds__(TILE_PIX) blend_backward_kernel(
-	const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const float4* __restrict__ rec, int W, int H,
-	const float* __restrict__ bg, const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
-	const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dalpha_map,
-	const float* __restrict__ dL_dfeat, float* __restrict__ grec)
+__global__ void __launch_bounds__(BLEND_WARPS * 32) blend_backward_kernel(
+	const uint2* ranges, const uint32_t* order, const uint32_t* point_list, const float4* rec,
+	int W, int H, int grid_x, uint32_t units, unsigned int* ticket, unsigned int* exits,
+	const float* __restrict__ bg, const float* final_T, const uint32_t* n_contrib, const float* __restrict__ dL_dcolor,
+	const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dalpha_map, const float* __restrict__ dL_dfeat,
+	float* __restrict__ grec)
 {
 	constexpr int NC = EXT ? 8 : 3;
-	__shared__ float4 s_g0[TILE_PIX], s_g1[TILE_PIX], s_g2[TILE_PIX];
-	__shared__ float4 s_g3[EXT ? TILE_PIX : 1];
-	__shared__ uint32_t s_id[TILE_PIX];
-	__shared__ __align__(16) float s_acc[TILE_PIX * GREC_FLOATS];
-	__shared__ uint32_t s_max[TILE_PIX / 32];
-
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int bx = (warp & 1) * 8, by = (warp >> 1) * 4;
-	const unsigned px = blockIdx.x * TILE_X + bx + (lane & 7), py = blockIdx.y * TILE_Y + by + (lane >> 3);
-	const bool inside = px < (unsigned)W && py < (unsigned)H;
-	const float pxf = (float)px, pyf = (float)py;
-	PixelBlock pb;
-	pb.X0 = (float)(blockIdx.x * TILE_X + bx); pb.X1 = pb.X0 + 7.f;
-	pb.Y0 = (float)(blockIdx.y * TILE_Y + by); pb.Y1 = pb.Y0 + 3.f;
-	const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
-	const size_t pix = (size_t)py * W + px, HW = (size_t)H * W;
-
-	const float T_final = inside ? final_T[pix] : 0.f;
-	float T = T_final;
-	const uint32_t last_contributor = inside ? n_contrib[pix] : 0u;
-	float dpix[NC];
-#pragma unroll
-	for (int ch = 0; ch < NC; ch++) dpix[ch] = 0.f;
-	if (inside) {
-		if (dL_dcolor) { dpix[0] = dL_dcolor[pix]; dpix[1] = dL_dcolor[HW + pix]; dpix[2] = dL_dcolor[2 * HW + pix]; }
-		if (EXT) {
-			if (dL_ddepth) dpix[3] = dL_ddepth[pix];
-			if (dL_dalpha_map) dpix[4] = dL_dalpha_map[pix];
-			if (dL_dfeat) { dpix[5] = dL_dfeat[pix]; dpix[6] = dL_dfeat[HW + pix]; dpix[7] = dL_dfeat[2 * HW + pix]; }
-		}
-	}
-	const float bg_dot_dpixel = __ldg(bg) * dpix[0] + __ldg(bg + 1) * dpix[1] + __ldg(bg + 2) * dpix[2];
+	constexpr int NACC = EXT ? 7 : 6;  // accumulators per phase-2 lane (6 moments / 7 or 3 channel sums)
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	BwdSmem<EXT>& S = reinterpret_cast<BwdSmem<EXT>*>(smem_raw)[threadIdx.x >> 5];
+	const unsigned lane = threadIdx.x & 31;
+	pdl_trigger();
+	pdl_wait();
+	const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
 	const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+	const Ticket tk{ticket, exits};
+	{  // pixel-moment half of the basis table: the same for every unit
+		const float cx = (float)(lane & 7), cy = (float)(lane >> 3);
+		S.basis[lane][0][0] = make_float4(1.f, cx, cy, cx * cx);
+		S.basis[lane][0][1] = make_float4(cx * cy, cy * cy, 0.f, 0.f);
+	}
 
-	// entries at list positions >= max(n_contrib) over the tile are never replayed (backward.cu:487-488)
-	uint32_t wmax = last_contributor;
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xFFFFFFFFu, wmax, o));
-	if (lane == 0) s_max[warp] = wmax;
-	__syncthreads();
-	uint32_t tmax = 0;
-#pragma unroll
-	for (int w = 0; w < TILE_PIX / 32; w++) tmax = max(tmax, s_max[w]);
-	const int n = (int)tmax;  // <= range.y - range.x
+	for (uint32_t unit = tk.next(lane); unit < units; unit = tk.next(lane)) {
+		const Unit u = make_unit(unit, order, ranges, W, H, grid_x);
+		const size_t pix = (size_t)u.py * W + u.px, HW = (size_t)H * W;
 
-	float accum_rec[NC], last_color[NC];
+		// everything the unit needs from the image planes is requested at once, ahead of the wmax == 0 test
+		const float T_final = u.inside ? __ldcg(final_T + pix) : 0.f;
+		float T = T_final;
+		const uint32_t last_contributor = u.inside ? __ldcg(n_contrib + pix) : 0u;
+		float dpix[NC];
 #pragma unroll
-	for (int ch = 0; ch < NC; ch++) { accum_rec[ch] = 0.f; last_color[ch] = 0.f; }
-	float last_alpha = 0.f;
-
-	const int nbatch = (n + TILE_PIX - 1) / TILE_PIX;
-	for (int b = nbatch - 1; b >= 0; b--) {
-		const int base = b * TILE_PIX;
-		const int cnt = min(TILE_PIX, n - base);
-		__syncthreads();  // previous batch fully flushed
-		if (tid < cnt) {
-			const uint32_t id = point_list[range.x + base + tid];
-			s_id[tid] = id;
-			const float4* r = rec + 4 * (size_t)id;
-			s_g0[tid] = __ldg(r); s_g1[tid] = __ldg(r + 1); s_g2[tid] = __ldg(r + 2);
-			if (EXT) s_g3[tid] = __ldg(r + 3);
-		}
-#pragma unroll
-		for (int k = 0; k < GREC_FLOATS / 4; k++)
-			reinterpret_cast<float4*>(s_acc)[k * TILE_PIX + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
-		__syncthreads();
-
-		if ((int)wmax > base) {
-			for (int m = (cnt - 1) / 32; m >= 0; m--) {
-				const int jj = m * 32 + lane;
-				bool keep = false;
-				if (jj < cnt && (uint32_t)(base + jj) < wmax) keep = !cull_block(s_g0[jj], s_g1[jj], pb);
-				unsigned mask = __ballot_sync(0xFFFFFFFFu, keep);
-				while (mask) {
-					const int bit = 31 - __clz(mask);
-					mask &= ~(1u << bit);
-					const int j = m * 32 + bit;
-					const float4 g0 = s_g0[j];
-					const float4 g1 = s_g1[j];
-					const float dx = __fsub_rn(g0.x, pxf), dy = __fsub_rn(g0.y, pyf);
-					const float power = pair_power(dx, dy, g0.z, g0.w, g1.x);
-					const float G = expf(power);
-					const float alpha = fminf(0.99f, __fmul_rn(g1.y, G));
-					const bool active = ((uint32_t)(base + j) < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-					if (!__any_sync(0xFFFFFFFFu, active)) continue;
-					float v[16];
-#pragma unroll
-					for (int k = 0; k < 16; k++) v[k] = 0.f;
-					if (active) {
-						T = T / (1.f - alpha);
-						const float dchannel_dcolor = alpha * T;
-						const float4 g2 = s_g2[j];
-						float col[NC];
-						col[0] = g2.x; col[1] = g2.y; col[2] = g2.z;
-						if (EXT) {
-							const float4 g3 = s_g3[j];
-							col[3] = g2.w; col[4] = 1.0f; col[5] = g3.x; col[6] = g3.y; col[7] = g3.z;
-						}
-						float dL_dalpha = 0.0f;
-#pragma unroll
-						for (int ch = 0; ch < NC; ch++) {
-							accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
-							last_color[ch] = col[ch];
-							dL_dalpha += (col[ch] - accum_rec[ch]) * dpix[ch];
-						}
-						dL_dalpha *= T;
-						last_alpha = alpha;
-						dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
-						const float dL_dG = g1.y * dL_dalpha;  // min(0.99,.) clamp ignored in backward (backward.cu:538)
-						const float gdx = G * dx, gdy = G * dy;
-						const float dG_ddelx = -gdx * g0.z - gdy * g0.w;
-						const float dG_ddely = -gdy * g1.x - gdx * g0.w;
-						v[0] = dL_dG * dG_ddelx * ddelx_dx;
-						v[1] = dL_dG * dG_ddely * ddely_dy;
-						v[2] = -0.5f * gdx * dx * dL_dG;
-						v[3] = -0.5f * gdx * dy * dL_dG;
-						v[4] = -0.5f * gdy * dy * dL_dG;
-						v[5] = G * dL_dalpha;
-						v[6] = dchannel_dcolor * dpix[0];
-						v[7] = dchannel_dcolor * dpix[1];
-						v[8] = dchannel_dcolor * dpix[2];
-						if (EXT) {
-							v[9] = dchannel_dcolor * dpix[3];
-							v[10] = dchannel_dcolor * dpix[5];
-							v[11] = dchannel_dcolor * dpix[6];
-							v[12] = dchannel_dcolor * dpix[7];
-						}
-					}
-					const float tot = warp_reduce_scatter16(v, lane);
-					if ((lane & 1) == 0 && (lane >> 1) < (EXT ? 13 : 9)) atomicAdd(&s_acc[j * GREC_FLOATS + (lane >> 1)], tot);
-				}
+		for (int ch = 0; ch < NC; ch++) dpix[ch] = 0.f;
+		if (u.inside) {
+			if (dL_dcolor) { dpix[0] = __ldcg(dL_dcolor + pix); dpix[1] = __ldcg(dL_dcolor + HW + pix); dpix[2] = __ldcg(dL_dcolor + 2 * HW + pix); }
+			if (EXT) {
+				if (dL_ddepth) dpix[3] = __ldcg(dL_ddepth + pix);
+				if (dL_dalpha_map) dpix[4] = __ldcg(dL_dalpha_map + pix);
+				if (dL_dfeat) { dpix[5] = __ldcg(dL_dfeat + pix); dpix[6] = __ldcg(dL_dfeat + HW + pix); dpix[7] = __ldcg(dL_dfeat + 2 * HW + pix); }
 			}
 		}
-		__syncthreads();
-		if (tid < cnt) {
-			const float4* a = reinterpret_cast<const float4*>(s_acc) + 4 * tid;
-			const float4 a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3];
-			float* dst = grec + (size_t)s_id[tid] * GREC_FLOATS;
-			if (a0.x != 0.f || a0.y != 0.f || a0.z != 0.f || a0.w != 0.f) red_add_v4(dst, a0.x, a0.y, a0.z, a0.w);
-			if (a1.x != 0.f || a1.y != 0.f || a1.z != 0.f || a1.w != 0.f) red_add_v4(dst + 4, a1.x, a1.y, a1.z, a1.w);
-			if (a2.x != 0.f || a2.y != 0.f || a2.z != 0.f || a2.w != 0.f) red_add_v4(dst + 8, a2.x, a2.y, a2.z, a2.w);
-			if (EXT && (a3.x != 0.f)) red_add_v4(dst + 12, a3.x, a3.y, a3.z, a3.w);
+		uint32_t wmax = last_contributor;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xFFFFFFFFu, wmax, o));
+		if (wmax == 0) continue;  // nothing was blended into this block
+
+		// cotangents of the channels that own a per-Gaussian gradient: r,g,b,z | f0,f1,f2
+		S.basis[lane][1][0] = make_float4(dpix[0], dpix[1], dpix[2], EXT ? dpix[3] : 0.f);
+		S.basis[lane][1][1] = EXT ? make_float4(dpix[5], dpix[6], dpix[7], 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+		const float bg_dot_dpixel = bg0 * dpix[0] + bg1 * dpix[1] + bg2 * dpix[2];
+		float A = 0.f, lastD = 0.f, last_alpha = 0.f;
+
+		Walk<false> wk;
+		wk.list = point_list + u.range.x; wk.rec = rec; wk.n = (int)wmax; wk.top = (int)wmax - 1; wk.lane = lane;
+		const int R = (wk.n + 31) >> 5;
+
+		// One batch: `count` staged survivors at ring slots base.. (base % 16 == 0), deepest first; `cpad` = count rounded
+		// up to even (an odd tail is padded with an inert survivor).
+		auto process = [&](int base, int count, int cpad) {
+			// ---- phase 1: lane = pixel.  The reference's per-channel accum_rec recurrence (backward.cu:509-516) is
+			// carried as one scalar, A = sum_ch accum_rec[ch] * dL/dpixel[ch].
+			float* wrow = &S.w[0][lane * WSTRIDE];
+			for (int k0 = 0; k0 < cpad; k0 += 2) {
+				float Gk[2], al[2], op[2];
+				bool act[2];
+#pragma unroll
+				for (int k = 0; k < 2; k++) {
+					const float4 a = S.g0[base + k0 + k];
+					const float4 b = S.g1[base + k0 + k];
+					const float dx = __fsub_rn(a.x, u.pxf), dy = __fsub_rn(a.y, u.pyf);
+					const float power = pair_power(dx, dy, a.z, a.w, b.x);
+					op[k] = b.y;
+					Gk[k] = expf(power);
+					al[k] = fminf(0.99f, __fmul_rn(b.y, Gk[k]));
+					act[k] = (S.pos[base + k0 + k] <= last_contributor) && !(power > 0.0f) && !(al[k] < 1.0f / 255.0f);
+				}
+#pragma unroll
+				for (int k = 0; k < 2; k++) {
+					float wg = 0.f, wc = 0.f;
+					if (act[k]) {
+						const float alpha = al[k];
+						const float inv = rcp_approx(1.0f - alpha);
+						T *= inv;
+						const float4 c = S.g2[base + k0 + k];
+						float D = c.x * dpix[0] + c.y * dpix[1] + c.z * dpix[2];
+						if (EXT) {
+							const float4 f = S.g3[base + k0 + k];
+							D += c.w * dpix[3] + dpix[4] + f.x * dpix[5] + f.y * dpix[6] + f.z * dpix[7];
+						}
+						A = last_alpha * lastD + (1.f - last_alpha) * A;
+						lastD = D;
+						last_alpha = alpha;
+						const float dL_dalpha = (D - A) * T - (T_final * inv) * bg_dot_dpixel;
+						wg = Gk[k] * (op[k] * dL_dalpha);  // G * dL/dG; clamp ignored as in backward.cu:538
+						wc = alpha * T;
+					}
+					wrow[k0 + k] = wg;
+					wrow[32 * WSTRIDE + 16 + k0 + k] = wc;  // S.w[1]
+				}
+			}
+			__syncwarp();
+			// ---- phase 2: lane = (half h, Gaussian g).  h = 0: pixel moments of wg; h = 1: channel sums of wc.
+			const int g = (int)(lane & 15u), h = (int)(lane >> 4);
+			if (g < count) {
+				float acc[NACC];
+#pragma unroll
+				for (int k = 0; k < NACC; k++) acc[k] = 0.f;
+				const float* wcol = S.w[h] + g;
+#pragma unroll
+				for (int p = 0; p < 32; p++) {
+					const float wv = wcol[p * WSTRIDE];
+					const float4 b0 = S.basis[p][h][0];
+					acc[0] = fmaf(wv, b0.x, acc[0]); acc[1] = fmaf(wv, b0.y, acc[1]); acc[2] = fmaf(wv, b0.z, acc[2]);
+					acc[3] = fmaf(wv, b0.w, acc[3]);
+					const float4 b1 = S.basis[p][h][1];
+					acc[4] = fmaf(wv, b1.x, acc[4]); acc[5] = fmaf(wv, b1.y, acc[5]);
+					if (EXT) acc[6] = fmaf(wv, b1.z, acc[6]);
+				}
+				bool any = false;
+#pragma unroll
+				for (int k = 0; k < NACC; k++) any = any || (acc[k] != 0.f);
+				if (any) {
+					float* dst = grec + (size_t)S.id[base + g] * GREC_FLOATS + 8 * h;
+					if (h == 0) {
+						const float4 a = S.g0[base + g];
+						const float4 b = S.g1[base + g];
+						const float S0 = acc[0], Cx = acc[1], Cy = acc[2], Cxx = acc[3], Cxy = acc[4], Cyy = acc[5];
+						const float ex = a.x - u.pb.X0, ey = a.y - u.pb.Y0;  // d = mean - pixel = (ex - cx, ey - cy)
+						const float Sx = ex * S0 - Cx, Sy = ey * S0 - Cy;
+						const float Sxx = ex * (ex * S0 - 2.f * Cx) + Cxx;
+						const float Syy = ey * (ey * S0 - 2.f * Cy) + Cyy;
+						const float Sxy = ex * (ey * S0 - Cy) - ey * Cx + Cxy;
+						red_add_v4(dst, -(a.z * Sx + a.w * Sy) * ddelx_dx, -(b.x * Sy + a.w * Sx) * ddely_dy, -0.5f * Sxx, -0.5f * Sxy);
+						red_add_v4(dst + 4, -0.5f * Syy, S0 / b.y, 0.f, 0.f);
+					} else {
+						red_add_v4(dst, acc[0], acc[1], acc[2], acc[3]);
+						if (EXT) red_add_v4(dst + 4, acc[4], acc[5], acc[6], 0.f);
+					}
+				}
+			}
+			__syncwarp();
+		};
+
+		float4 ga0, ga1, gb0, gb1;
+		ga0 = ga1 = gb0 = gb1 = make_float4(0.f, 0.f, 0.f, 0.f);
+		uint32_t ida = wk.load_id(0), idb = wk.load_id(1), idc = wk.load_id(2);
+		wk.load_geo(ida, ga0, ga1);
+		wk.load_geo(idb, gb0, gb1);
+		int head = 0, tail = 0;
+		int hist[K_INFLIGHT + 1];
+#pragma unroll
+		for (int j = 0; j <= K_INFLIGHT; j++) hist[j] = 0;
+		__syncwarp();  // basis visible
+		for (int r = 0; r < R; r++) {
+			const uint32_t idd = wk.load_id(r + 3);
+			float4 gc0 = make_float4(0.f, 0.f, 0.f, 0.f), gc1 = gc0;
+			wk.load_geo(idc, gc0, gc1);
+			cp_wait<K_INFLIGHT>();
+			if (hist[K_INFLIGHT] - tail >= BATCH || head - tail > RING - 32) {
+				if (head - tail > RING - 32) { cp_wait<0>(); hist[K_INFLIGHT] = head; }
+				__syncwarp();
+				do { process(tail & (RING - 1), BATCH, BATCH); tail += BATCH; } while (hist[K_INFLIGHT] - tail >= BATCH);
+			}
+			head += wk.template stage<EXT, true>(S, r, ida, ga0, ga1, u.pb, head);
+			cp_commit();
+#pragma unroll
+			for (int j = K_INFLIGHT; j > 0; j--) hist[j] = hist[j - 1];
+			hist[0] = head;
+			ga0 = gb0; ga1 = gb1; gb0 = gc0; gb1 = gc1;
+			ida = idb; idb = idc; idc = idd;
+		}
+		cp_wait<0>();
+		if (head > tail) {
+			if ((head & 1) && lane == 0) {  // inert survivor after an odd tail: never active (position beyond every n_contrib)
+				const int slot = head & (RING - 1);
+				const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+				S.g0[slot] = z; S.g1[slot] = z;
+				S.pos[slot] = 0xFFFFFFFFu;
+			}
+			__syncwarp();
+			while (head > tail) {
+				const int c = min(BATCH, head - tail);
+				process(tail & (RING - 1), c, (c + 1) & ~1);
+				tail += c;
+			}
 		}
 	}
+	tk.leave(lane, gridDim.x * BLEND_WARPS);
+}
+
+// One persistent wave: as many CTAs as fit on the device (occupancy x SM count), never more than there are units.
+template <typename K>
+unsigned persistent_cap(K kernel, size_t smem, int limit) {
+	int dev = 0, sms = 0, per_sm = 0;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BLEND_WARPS * 32, smem);
+	if (per_sm < 1) per_sm = 1;
+	if (sms < 1) sms = 148;
+	if (limit > 0 && per_sm > limit) per_sm = limit;
+	return (unsigned)(per_sm * sms);
+}
+
+// CTAs per SM of the persistent grids (forward, backward).  Fewer resident warps than units lets the ticket balance the
+// SMs; more warps hide more latency.  Defaults measured on B200; B200GS_BLEND_CTAS=f,b overrides for A/B runs.
+int ctas_per_sm(int dir) {
+	static int v[2] = {-1, -1};
+	if (v[0] < 0) {
+		v[0] = B200GS_FWD_CTAS; v[1] = B200GS_BWD_CTAS;
+		if (const char* e = getenv("B200GS_BLEND_CTAS")) {
+			int a = 0, b = 0;
+			if (sscanf(e, "%d,%d", &a, &b) == 2) { v[0] = a; v[1] = b; }
+		}
+	}
+	return v[dir];
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_blend(unsigned site, void (*kernel)(KArgs...), unsigned grid, size_t smem, cudaStream_t stream, Args&&... args) {
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(grid);
+	cfg.blockDim = dim3(BLEND_WARPS * 32);
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = (site & pdl_mask()) ? 1 : 0;
+	return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 }  // namespace
 
-void launch_blend_forward_tile(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
+void launch_blend_forward(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
                           const b200gs_outputs_t& out, cudaStream_t stream) {
-	const dim3 grid((v.width + TILE_X - 1) / TILE_X, (v.height + TILE_Y - 1) / TILE_Y);
-	if (v.extended)
-		blend_forward_kernel<true><<<grid, TILE_PIX, 0, stream>>>(is.ranges, bs.sorted_vals, gs.rec, v.width, v.height,
-			v.background, is.final_T, is.n_contrib, out.color, out.depth, out.alpha, out.feature);
-	else
-		blend_forward_kernel<false><<<grid, TILE_PIX, 0, stream>>>(is.ranges, bs.sorted_vals, gs.rec, v.width, v.height,
-			v.background, is.final_T, is.n_contrib, out.color, nullptr, nullptr, nullptr);
+	const int gx = (v.width + TILE_X - 1) / TILE_X, gy = (v.height + TILE_Y - 1) / TILE_Y;
+	const unsigned units = (unsigned)(gx * gy * 8);
+	unsigned int* ticket = &gs.hdr->blend_ticket[0];
+	unsigned int* exits = &gs.hdr->blend_exit[0];
+	if (v.extended) {
+		static unsigned cap = 0;
+		constexpr size_t smem = BLEND_WARPS * sizeof(FwdSmem<true>);
+		if (!cap) cap = persistent_cap(blend_forward_kernel<true>, smem, ctas_per_sm(0));
+		const unsigned want = (units + BLEND_WARPS - 1) / BLEND_WARPS;
+		launch_blend(PDL_BLEND_FWD, blend_forward_kernel<true>, want < cap ? want : cap, smem, stream, (const uint2*)is.ranges,
+			(const uint32_t*)is.tile_order, (const uint32_t*)bs.sorted_vals, (const float4*)gs.rec,
+			v.width, v.height, gx, units, ticket, exits, v.background, is.final_T, is.n_contrib, out.color, out.depth, out.alpha, out.feature);
+	} else {
+		static unsigned cap = 0;
+		constexpr size_t smem = BLEND_WARPS * sizeof(FwdSmem<false>);
+		if (!cap) cap = persistent_cap(blend_forward_kernel<false>, smem, ctas_per_sm(0));
+		const unsigned want = (units + BLEND_WARPS - 1) / BLEND_WARPS;
+		launch_blend(PDL_BLEND_FWD, blend_forward_kernel<false>, want < cap ? want : cap, smem, stream, (const uint2*)is.ranges,
+			(const uint32_t*)is.tile_order, (const uint32_t*)bs.sorted_vals, (const float4*)gs.rec,
+			v.width, v.height, gx, units, ticket, exits, v.background, is.final_T, is.n_contrib, out.color, (float*)nullptr, (float*)nullptr, (float*)nullptr);
+	}
 	count_launch();
 }
 
-void launch_blend_backward_tile(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
+void launch_blend_backward(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
                            const b200gs_grad_outputs_t& gout, float* grec, cudaStream_t stream) {
-	const dim3 grid((v.width + TILE_X - 1) / TILE_X, (v.height + TILE_Y - 1) / TILE_Y);
-	if (v.extended)
-		blend_backward_kernel<true><<<grid, TILE_PIX, 0, stream>>>(is.ranges, bs.sorted_vals, gs.rec, v.width, v.height,
-			v.background, is.final_T, is.n_contrib, gout.dL_dcolor, gout.dL_ddepth, gout.dL_dalpha, gout.dL_dfeature, grec);
-	else
-		blend_backward_kernel<false><<<grid, TILE_PIX, 0, stream>>>(is.ranges, bs.sorted_vals, gs.rec, v.width, v.height,
-			v.background, is.final_T, is.n_contrib, gout.dL_dcolor, nullptr, nullptr, nullptr, grec);
+	const int gx = (v.width + TILE_X - 1) / TILE_X, gy = (v.height + TILE_Y - 1) / TILE_Y;
+	const unsigned units = (unsigned)(gx * gy * 8);
+	unsigned int* ticket = &gs.hdr->blend_ticket[1];
+	unsigned int* exits = &gs.hdr->blend_exit[1];
+	// first kernel of the backward chain: its predecessor is a memset / the caller's loss kernels, so no programmatic launch
+	if (v.extended) {
+		static unsigned cap = 0;
+		constexpr size_t smem = BLEND_WARPS * sizeof(BwdSmem<true>);
+		if (!cap) cap = persistent_cap(blend_backward_kernel<true>, smem, ctas_per_sm(1));
+		const unsigned want = (units + BLEND_WARPS - 1) / BLEND_WARPS;
+		launch_blend(0u, blend_backward_kernel<true>, want < cap ? want : cap, smem, stream, (const uint2*)is.ranges,
+			(const uint32_t*)is.tile_order, (const uint32_t*)bs.sorted_vals, (const float4*)gs.rec,
+			v.width, v.height, gx, units, ticket, exits, v.background, (const float*)is.final_T, (const uint32_t*)is.n_contrib,
+			gout.dL_dcolor, gout.dL_ddepth, gout.dL_dalpha, gout.dL_dfeature, grec);
+	} else {
+		static unsigned cap = 0;
+		constexpr size_t smem = BLEND_WARPS * sizeof(BwdSmem<false>);
+		if (!cap) cap = persistent_cap(blend_backward_kernel<false>, smem, ctas_per_sm(1));
+		const unsigned want = (units + BLEND_WARPS - 1) / BLEND_WARPS;
+		launch_blend(0u, blend_backward_kernel<false>, want < cap ? want : cap, smem, stream, (const uint2*)is.ranges,
+			(const uint32_t*)is.tile_order, (const uint32_t*)bs.sorted_vals, (const float4*)gs.rec,
+			v.width, v.height, gx, units, ticket, exits, v.background, (const float*)is.final_T, (const uint32_t*)is.n_contrib,
+			gout.dL_dcolor, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, grec);
+	}
 	count_launch();
 }

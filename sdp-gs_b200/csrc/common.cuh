@@ -16,7 +16,8 @@
 //   g3 = {f0, f1, f2, 0}                                         (SDP-GS feature head)
 #define REC_FLOATS 16
 // Per-Gaussian gradient record accumulated by the blend backward (64 bytes):
-//   {dmean2D.x, dmean2D.y, dconic.a, dconic.b | dconic.c, dopacity, dr, dg | db, dz, df0, df1 | df2, -, -, -}
+//   {dmean2D.x, dmean2D.y, dconic.a, dconic.b | dconic.c, dopacity, -, - | dr, dg, db, dz | df0, df1, df2, -}
+// (first half: pixel moments of G*dL/dG, second half: channel sums of alpha*T -- written by different half-warps)
 #define GREC_FLOATS 16
 
 struct GeomHeader {  // first 256 bytes of the geom workspace
@@ -26,7 +27,9 @@ struct GeomHeader {  // first 256 bytes of the geom workspace
 	unsigned int sort_ticket[8];      // one per radix pass (4 depth passes + up to 4 tile passes)
 	unsigned int ranges_done;         // CTAs of the tile-ranges kernel that have finished (last one builds the blend schedule)
 	unsigned int emit_done;           // CTAs of scan_emit that have finished (last one turns tile counts into ranges + schedule)
-	unsigned int pad[50];
+	unsigned int blend_ticket[2];     // next blend unit to hand out (forward, backward): persistent warps draw from it
+	unsigned int blend_exit[2];       // warps that have run dry; the last one re-arms ticket and counter
+	unsigned int pad[46];
 };
 static_assert(sizeof(GeomHeader) == 256, "header size");
 

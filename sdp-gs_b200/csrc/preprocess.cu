@@ -443,9 +443,9 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_backward_kernel(
 	const float4 g0 = s_grec[4 * li], g1 = s_grec[4 * li + 1], g2 = s_grec[4 * li + 2], g3 = s_grec[4 * li + 3];
 	const float dm2x = g0.x, dm2y = g0.y, dca = g0.z, dcb = g0.w, dcc = g1.x;
 	float dop = g1.y;
-	dRGB[0] = g1.z; dRGB[1] = g1.w; dRGB[2] = g2.x;
-	const float dz = g2.y;
-	const float df[3] = {g2.z, g2.w, g3.x};
+	dRGB[0] = g2.x; dRGB[1] = g2.y; dRGB[2] = g2.z;
+	const float dz = g2.w;
+	const float df[3] = {g3.x, g3.y, g3.z};
 
 	const float mx = s_means[3 * li], my = s_means[3 * li + 1], mz = s_means[3 * li + 2];
 
