@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--P", type=int, default=None, help="override the Gaussian count of the workload")
     ap.add_argument("--fwd-only", action="store_true", help="forward only (render throughput, BASELINE configs[3])")
     ap.add_argument("--no-train", action="store_true", help="skip the training-iteration measurement (`train` key)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the two sharded-path measurements of BASELINE.json configs[3]/[4] "
+                                                               "(`render_sharded`, `stress_train` keys)")
     return ap.parse_args()
 
 
@@ -128,10 +130,10 @@ def peaks():
 
 
 class Workload:
-    def __init__(self, name, mode, dev, P=None):
+    def __init__(self, name, mode, dev, P=None, views=None, with_cot=True):
         self.name, self.mode, self.dev = name, mode, dev
         cfg = syn.CONFIGS[name]
-        sc = syn.make_config(name, P=P, views=min(cfg["views"], 8))
+        sc = syn.make_config(name, P=P, views=views or min(cfg["views"], 8))
         self.scene = sc
         self.extended = mode == "extended"
         self.W, self.H = cfg["width"], cfg["height"]
@@ -144,7 +146,7 @@ class Workload:
         self.cams = sc.cameras
         self.bg = torch.zeros(3, device=dev)
         self.cot = []
-        for i, cam in enumerate(self.cams):
+        for i, cam in enumerate(self.cams if with_cot else []):
             self.cot.append(tuple(torch.from_numpy(c).to(dev) for c in syn.cotangents(cam, 100 + i)))
 
     def settings(self, cam, P):
@@ -207,6 +209,187 @@ def wall_loop(K, warmup, step_fn, world):
 
 
 # ------------------------------------------------------------------------------------------ our arm
+def e2e_b200gs(args, wl, rank, world, dev):
+    """The metric through the public drop-in API (GaussianRasterizer + autograd) with HOST buffers: every step's parameters
+    are uploaded from pinned host memory (b200gs.hostio.PinnedFeeder: one copy per step on a copy stream, step i+1's upload
+    overlapping step i's kernels) and the step's result is read back.  Returns (views/s, seconds, H2D bytes per step)."""
+    from b200gs import rasterizer as rz
+    from b200gs.hostio import PinnedFeeder
+    from diff_gaussian_rasterization import GaussianRasterizer
+    P, ext, nviews = wl.scene.P, wl.extended, len(wl.cams)
+    feeder = PinnedFeeder(wl.host, dev)
+    settings = [wl.settings(cam, P) for cam in wl.cams]
+
+    def body(vi, t):
+        means2D = torch.zeros((P, 3), device=dev, requires_grad=True)
+        kw = dict(means3D=t["means3D"], means2D=means2D, opacities=t["opacities"], shs=t["shs"], scales=t["scales"],
+                  rotations=t["rotations"])
+        if ext:
+            kw["language_feature_precomp"] = t["features"]
+        if args.fwd_only:
+            with torch.no_grad():
+                outs = GaussianRasterizer(settings[vi])(**kw)
+            return float(outs[0].sum().item())
+        outs = GaussianRasterizer(settings[vi])(**kw)
+        cot = wl.cot[vi]
+        # the loss lives outside the rasterizer: its gradient w.r.t. the rendered maps is handed to autograd directly
+        torch.autograd.backward(list(outs[:4]) if ext else [outs[0]], list(cot) if ext else [cot[0]])
+        if world > 1:
+            g = torch.cat([t[k].grad.reshape(-1) for k in sorted(t)])
+            dist.all_reduce(g)
+        return float(outs[0].sum().item())  # the step's result read back to the host
+
+    def step(i):
+        t = {k: v.requires_grad_(True) for k, v in feeder.next().items()}
+        try:
+            return body((i + rank) % nviews, t)
+        finally:
+            feeder.done()
+
+    rz.set_binning_capacity("auto")  # public knob: learned capacity, no host sync inside the forward after the first call
+    try:
+        sec = wall_loop(args.steps, max(3, args.warmup), step, world)
+        rz._check_pending(block=True)
+    finally:
+        rz.set_binning_capacity(None)
+    return world * args.steps / sec, sec, feeder.nbytes
+
+
+def collective_check(wl, sessions, bucket, capacity, rank, world):
+    """Correctness evidence for the gradient exchange inside the timed step (N > 1): this rank's view through the step's own
+    path (reduce-scatter inside the backward kernel + gather kernel, or the two-shot all-reduce kernel) against the same
+    gradients computed locally and summed by NCCL."""
+    from b200gs import parallel
+    from b200gs import rasterizer as rz
+    P, ext = wl.scene.P, wl.extended
+    vi = rank % len(wl.cams)
+    plain = parallel.FusedGradBuffer(P, wl.dev, symmetric=False)
+    go = dict(means3D=plain.segment("xyz"), shs=plain.segment("shs"), opacities=plain.segment("opacity"), scales=plain.segment("scaling"),
+              rotations=plain.segment("rotation"))
+    if ext:
+        go["features"] = plain.segment("language_feature")
+    sp = rz.RasterSession(wl.settings(wl.cams[vi], P), means3D=wl.devt["means3D"], opacities=wl.devt["opacities"], shs=wl.devt["shs"],
+                          scales=wl.devt["scales"], rotations=wl.devt["rotations"], language_feature_precomp=wl.devt.get("features"),
+                          extended=ext, capacity=capacity, grads_out=go)
+    for k in sp.cot:
+        sp.cot[k].copy_(sessions[vi].cot[k])
+    sp.step()
+    ref = plain.grads_flat.clone()
+    dist.all_reduce(ref)
+    bucket.flat.fill_(float("nan"))
+    sessions[vi].step()
+    if bucket.fused_exchange:
+        bucket.gather_reduce()
+    else:
+        bucket.all_reduce()
+    torch.cuda.synchronize()
+    worst, c = 0.0, 0
+    for k, w in parallel.SLOTS[:6]:
+        if k == "language_feature" and not ext:
+            c += w
+            continue
+        want = ref[c * plain.Pp:c * plain.Pp + w * P].view(P, w)
+        mine = bucket.segment(k).reshape(P, -1)
+        worst = max(worst, float((mine - want).abs().max()) / max(float(want.abs().max()), 1e-30))
+        c += w
+    chk = torch.stack([bucket.segment(k).double().nan_to_num().sum() for k, _ in parallel.SLOTS[:5]]).sum().reshape(1)
+    lst = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(lst, chk)
+    return dict(path="reduce-scatter inside preprocess-backward + gather kernel" if bucket.fused_exchange else "two-shot all-reduce kernel",
+                against="local gradients + NCCL all_reduce(SUM)", max_rel_err=worst,
+                identical_on_all_ranks=all(float(x) == float(lst[0]) for x in lst))
+
+
+def render_sharded(args, rank, world, dev, flush):
+    """BASELINE.json configs[3]: 3M Gaussians at 1297x840, 200 test views, forward only, rank r renders views r::N
+    (render.py:38-39; no collective in the loop).  One RasterSession; the camera matrices are swapped in place per view."""
+    from b200gs import rasterizer as rz
+    nv = 200
+    wl = Workload("mip360_render", "extended", dev, views=nv, with_cot=False)
+    P = wl.scene.P
+    Ls = []
+    for cam in wl.cams[:: max(1, nv // 4)]:  # instance counts of a few views spread over the orbit size the binning workspace
+        rs = wl.settings(cam, P)
+        res = rz._forward_impl(rs, wl.devt["means3D"], wl.devt["shs"], None, wl.devt["opacities"], wl.devt["scales"], wl.devt["rotations"],
+                               None, None, wl.devt["features"], getattr(rs, "confidence", None), True)
+        Ls.append(res[0])
+        del res
+    cap = int(max(Ls) * 1.4) + 4096
+    rs0 = wl.settings(wl.cams[0], P)
+    s = rz.RasterSession(rs0, means3D=wl.devt["means3D"], opacities=wl.devt["opacities"], shs=wl.devt["shs"], scales=wl.devt["scales"],
+                         rotations=wl.devt["rotations"], language_feature_precomp=wl.devt["features"], extended=True, capacity=cap,
+                         with_backward=False)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    mine = list(range(rank, nv, world))
+    vm = torch.stack([t(wl.cams[i].viewmatrix) for i in mine]); pm = torch.stack([t(wl.cams[i].projmatrix) for i in mine])
+    cp = torch.stack([t(wl.cams[i].campos) for i in mine])
+    cams = torch.cat([vm.reshape(len(mine), -1), pm.reshape(len(mine), -1), cp.reshape(len(mine), -1)], dim=1).contiguous()  # [n, 35]
+    live = torch.zeros((35,), device=dev)  # the session's view points at these three slices
+    s.v.viewmatrix, s.v.projmatrix, s.v.campos = live.data_ptr(), live[16:].data_ptr(), live[32:].data_ptr()
+    checksum = torch.zeros((), device=dev, dtype=torch.float64)
+
+    def render_all():
+        for j in range(len(mine)):
+            live.copy_(cams[j])
+            s.forward()
+            checksum.add_(s.color[0, 0, 0].double())  # every view's image is consumed
+
+    render_all()  # warm-up pass over this rank's views
+    assert s.status()[1] == 0, "binning capacity overflow in render_sharded"
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); render_all(); e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    assert s.status()[1] == 0, "binning capacity overflow in render_sharded"
+    return dict(workload=f"mip360_render: P={P}, 1297x840, {nv} views forward only, rank r renders views r::{world} (no collective)",
+                views_per_s=nv * 1000.0 / ms, ms_per_view_per_gpu=ms / len(mine), total_ms=ms, views=nv, num_rendered_sample=int(np.mean(Ls)),
+                timing="CUDA events around one pass over the rank's views, max over ranks; L2 not flushed (every view streams > 1 GB)")
+
+
+def stress_train(args, rank, world, dev, flush):
+    """BASELINE.json configs[4]: 6M Gaussians at 1920x1080, 8 views per optimizer step split over the ranks (rank r takes views
+    r::N, gradients accumulate in the backward kernel at N < 8), one fused gradient exchange per step, ONE Adam step."""
+    from b200gs import rasterizer as rz
+    from b200gs.trainer import GaussianTrainer
+    wl = Workload("stress_train", "extended", dev, views=8, with_cot=False)
+    P = wl.scene.P
+    mine = list(range(rank, 8, world))
+    cams = [wl.cams[i] for i in mine]
+    Ls = []
+    for cam in cams:
+        rs = wl.settings(cam, P)
+        res = rz._forward_impl(rs, wl.devt["means3D"], wl.devt["shs"], None, wl.devt["opacities"], wl.devt["scales"], wl.devt["rotations"],
+                               None, None, wl.devt["features"], getattr(rs, "confidence", None), True)
+        Ls.append(res[0])
+        del res
+    cap = int(max(Ls) * 1.25) + 4096
+    rng = np.random.default_rng(4243)
+    gts = [rng.uniform(0, 1, size=(3, wl.H, wl.W)).astype(np.float32) for _ in cams]
+    monos = [rng.uniform(1, 8, size=(1, wl.H, wl.W)).astype(np.float32) for _ in cams]
+    rp = raw_params(wl.scene)
+    del wl.devt, wl.pinned
+    torch.cuda.empty_cache()
+    tr = GaussianTrainer(cameras=cams, gt_images=gts, depth_mono=monos, device=dev, capacity=cap, **rp)
+    tr.capture_multi(range(len(cams)))
+    steps = max(3, min(args.steps, 5))
+    ms, _ = event_loop(steps, 3, lambda i: tr.step_multi(), flush, world)
+    for sess in tr.sessions:
+        assert sess.status()[1] == 0, "binning capacity overflow in stress_train"
+    ms_it = ms / steps
+    return dict(workload=f"stress_train: P={P}, 1920x1080, 8 views per optimizer step ({len(cams)} per rank), losses + backward + "
+                         f"{'fused gradient exchange (62 floats per Gaussian) + ' if world > 1 else ''}Adam; one CUDA-graph replay per step",
+                steps_per_s=1000.0 / ms_it, views_per_s=8 * 1000.0 / ms_it, ms_per_step=ms_it, steps=steps,
+                exchange_bytes_per_rank=int(62 * 4 * tr.bucket.Pp * (world - 1) / world * 2) if world > 1 else 0,
+                num_rendered_mean=int(np.mean(Ls)), last_loss=tr.loss_values()[0])
+
+
 def run_b200gs(args, rank, world, local):
     from b200gs import _lib, parallel
     from b200gs import rasterizer as rz
@@ -219,6 +402,7 @@ def run_b200gs(args, rank, world, local):
     flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
     flush = lambda: flush_buf.zero_()
     own_ar = False
+    bucket_fused = False
 
     # instance counts per view (one synchronous forward each) -> capacity of the no-sync path
     Ls, Vs = [], []
@@ -240,15 +424,17 @@ def run_b200gs(args, rank, world, local):
         s = rz.RasterSession(wl.settings(cam, P), means3D=wl.devt["means3D"], opacities=wl.devt["opacities"], shs=wl.devt["shs"],
                              scales=wl.devt["scales"], rotations=wl.devt["rotations"],
                              language_feature_precomp=wl.devt.get("features"), extended=ext, capacity=capacity,
-                             grads_out=grads_out, with_backward=not args.fwd_only)
+                             grads_out=grads_out, with_backward=not args.fwd_only,
+                             grad_scatter=None if args.fwd_only else bucket.scatter_descriptor())
         if not args.fwd_only:
             s.cot["color"].copy_(wl.cot[vi][0])
             if ext:
                 s.cot["depth"].copy_(wl.cot[vi][1]); s.cot["alpha"].copy_(wl.cot[vi][2]); s.cot["feature"].copy_(wl.cot[vi][3])
         # our own all-reduce kernel (NVLink peer memory) is part of the captured step; an NCCL fallback stays outside the graph
         own_ar = world > 1 and not args.fwd_only and bucket._symm is not None
+        fused = bucket_fused = own_ar and bucket.fused_exchange  # reduce-scatter inside the backward kernel + gather kernel (default)
         if own_ar:
-            s.capture(fn=lambda s=s: (s.step(), bucket.all_reduce()))
+            s.capture(fn=lambda s=s: (s.step(), bucket.gather_reduce() if fused else bucket.all_reduce()))
         else:
             s.capture()
         sessions.append(s)
@@ -298,45 +484,7 @@ def run_b200gs(args, rank, world, local):
     stage_ms = {STAGES[i]: (ms[i] / nprof) for i in range(10)}
 
     # ---- end to end through the public API with host buffers
-    from b200gs.hostio import PinnedFeeder
-    feeder = PinnedFeeder(wl.host, dev)  # one pinned block; the upload of step i+1 overlaps the kernels of step i
-
-    def step_e2e(i):
-        vi = (i + rank) % nviews
-        t = {k: v.requires_grad_(True) for k, v in feeder.next().items()}
-        try:
-            return step_e2e_body(vi, t)
-        finally:
-            feeder.done()
-
-    def step_e2e_body(vi, t):
-        rs = wl.settings_cache[vi]
-        means2D = torch.zeros((P, 3), device=dev, requires_grad=True)
-        kw = dict(means3D=t["means3D"], means2D=means2D, opacities=t["opacities"], shs=t["shs"], scales=t["scales"],
-                  rotations=t["rotations"])
-        if ext:
-            kw["language_feature_precomp"] = t["features"]
-        if args.fwd_only:
-            with torch.no_grad():
-                outs = GaussianRasterizer(rs)(**kw)
-            return float(outs[0].sum().item())
-        outs = GaussianRasterizer(rs)(**kw)
-        cot = wl.cot[vi]
-        # the loss lives outside the rasterizer: its gradient w.r.t. the rendered maps is handed to autograd directly
-        torch.autograd.backward(list(outs[:4]) if ext else [outs[0]], list(cot) if ext else [cot[0]])
-        if world > 1:
-            g = torch.cat([t[k].grad.reshape(-1) for k in sorted(t)])
-            dist.all_reduce(g)
-        return float(outs[0].sum().item())  # the step's result read back to the host
-
-    wl.settings_cache = [wl.settings(cam, P) for cam in wl.cams]
-    rz.set_binning_capacity("auto")  # public knob: learned capacity, no host sync inside the forward after the first call
-    try:
-        e2e_sec = wall_loop(args.steps, max(3, args.warmup), step_e2e, world)
-        rz._check_pending(block=True)
-    finally:
-        rz.set_binning_capacity(None)
-    e2e_value = world * args.steps / e2e_sec
+    e2e_value, e2e_sec, feeder_bytes = e2e_b200gs(args, wl, rank, world, dev)
 
     # ---- vanilla single-call comparison point (colour only), device resident
     vanilla = None
@@ -349,7 +497,11 @@ def run_b200gs(args, rank, world, local):
             s.cot["color"].copy_(wv.cot[vi][0])
             sv.append(s.capture())
         vms, _ = event_loop(args.steps, args.warmup, lambda i: sv[i % nviews].replay(), flush, 1)
-        vanilla = dict(ms_per_view=vms / args.steps, views_per_s=1000.0 * args.steps / vms)
+        del sv
+        ve2e, vsec, vbytes = e2e_b200gs(args, wv, rank, world, dev)
+        vanilla = dict(ms_per_view=vms / args.steps, views_per_s=1000.0 * args.steps / vms,
+                       e2e=dict(value=ve2e, unit="views/s", ms_per_step=1000.0 * vsec / args.steps, h2d_bytes_per_step=vbytes,
+                                d2h_bytes_per_step=4 + 16))
 
     # ---- roofline of the dominant kernel + whole step
     L, V = int(np.mean(Ls)), int(np.mean(Vs))
@@ -386,9 +538,27 @@ def run_b200gs(args, rank, world, local):
     if not args.fwd_only and ext and not args.no_train:
         train = train_b200gs(args, wl, capacity, rank, world, flush)
 
+    coll = None
+    if world > 1 and not args.fwd_only and own_ar:
+        coll = collective_check(wl, sessions, bucket, capacity, rank, world)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(wl, 0)
+
+    # ---- the two sharded paths BASELINE.json names (configs[3], configs[4]); they need the memory the objects above hold
+    extras = {}
+    if not args.no_extras and not args.fwd_only and ext and args.workload == "llff_fern_3view" and args.P is None:
+        del sessions, bucket, grads_out, flush_buf
+        wl.devt = wl.pinned = None
+        torch.cuda.empty_cache()
+        small_flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+        for name, fn in (("render_sharded", render_sharded), ("stress_train", stress_train)):
+            try:
+                extras[name] = fn(args, rank, world, dev, lambda: small_flush.zero_())
+            except Exception as ex:  # never lose the headline line to an auxiliary measurement
+                extras[name] = dict(error=f"{type(ex).__name__}: {ex}")
+            torch.cuda.empty_cache()
 
     if rank == 0:
         line = dict(metric="rasterizer fwd+bwd views/s (1000/ms_per_step = ms/view; one view per train iteration)",
@@ -396,18 +566,18 @@ def run_b200gs(args, rank, world, local):
                     higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                     config=dict(workload=f"{args.workload}: P={P} Gaussians, {wl.W}x{wl.H}, SH degree 3 in-kernel, "
                                          f"outputs={'color+depth+alpha+feature' if ext else 'color'}, one view {'forward' if args.fwd_only else 'fwd+bwd'} per step"
-                                         + ((", per-Gaussian gradient all-reduce (image-parallel; " + ("own NVLink peer-memory kernel inside the graph" if own_ar else "NCCL") + ")") if world > 1 else ""),
+                                         + ((", per-Gaussian gradient all-reduce (image-parallel; " + (("reduce-scatter pushed over NVLink by the backward kernel + gather kernel, inside the graph" if bucket_fused else "own NVLink two-shot all-reduce kernel inside the graph") if own_ar else "NCCL") + ")") if world > 1 else ""),
                                 P=P, width=wl.W, height=wl.H, mode=args.mode, num_rendered=L, visible=V, tiles=model["tiles"],
                                 sort_passes_model=model["passes"], l2="flushed between steps (256 MiB write)",
                                 binning="capacity mode, CUDA graph replay", parallelism=f"image-parallel x{world}"),
                     e2e=dict(value=e2e_value, unit="views/s", ms_per_step=1000.0 * e2e_sec / args.steps,
-                             h2d_bytes_per_step=feeder.nbytes, d2h_bytes_per_step=4 + 16,
+                             h2d_bytes_per_step=feeder_bytes, d2h_bytes_per_step=4 + 16,
                              path="diff_gaussian_rasterization.GaussianRasterizer + torch.autograd.backward (binning capacity 'auto'); "
                                   "every step's parameters are uploaded from pinned host memory (b200gs.hostio.PinnedFeeder: one copy per "
                                   "step on a copy stream, step i+1's upload overlapping step i's kernels); color.sum().item() read back"),
                     gpu_launches=int(launches_per_step * args.steps), gpu_launches_per_step=int(launches_per_step),
                     clocks=clocks, roofline=roofline, cpu_baseline=cpu, vanilla=vanilla, train=train, impl="b200gs",
-                    wall_s=wall)
+                    collective_check=coll, wall_s=wall, **extras)
         print(json.dumps(line))
 
 
@@ -634,12 +804,17 @@ def run_reference(args, rank, world, local):
         vms, _ = event_loop(args.steps, args.warmup, lambda i: rb.step(i % nviews, wl.devt, False), flush, 1)
         vanilla = dict(ms_per_view=vms / args.steps, views_per_s=1000.0 * args.steps / vms)
 
-    def step_e2e(i):
-        T = {k: v.to(dev, non_blocking=True) for k, v in wl.pinned.items()}
-        rb.step(i % nviews, T, ext)
+    def step_e2e(i, extended=ext):
+        T = {k: v.to(dev, non_blocking=True) for k, v in wl.pinned.items() if extended or k != "features"}
+        rb.step(i % nviews, T, extended)
         return float(rb.color.sum().item())
 
     e2e_sec = wall_loop(args.steps, max(3, args.warmup), step_e2e, 1)
+    if vanilla is not None:  # the like-for-like single-call comparison, end to end as well
+        vsec = wall_loop(args.steps, max(3, args.warmup), lambda i: step_e2e(i, False), 1)
+        vanilla["e2e"] = dict(value=args.steps / vsec, unit="views/s", ms_per_step=1000.0 * vsec / args.steps,
+                              h2d_bytes_per_step=int(sum(v.numel() * 4 for k, v in wl.pinned.items() if k != "features")),
+                              d2h_bytes_per_step=4 + 4)
     train = None
     if ext and not args.fwd_only and not args.no_train:
         train = train_reference(args, wl, rb.bb, flush)

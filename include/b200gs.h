@@ -119,6 +119,22 @@ typedef struct b200gs_grads {
 	float* dL_dfeatures;      /* [P,3]   or NULL (language_feature_precomp) */
 	float* dL_dshs_language;  /* [P,3]   or NULL */
 	void* scratch;            /* P*64 bytes */
+	/* Image-parallel training (include/b200gs_collective.h): when scatter_bases != NULL the six parameter-gradient arrays
+	 * (means3D, shs [M = 16], opacities, scales, rotations, features / shs_language) are NOT written to the pointers above
+	 * but pushed, 128-Gaussian tile by tile, over NVLink into the staging buffer of the rank that owns the tile
+	 * (rank o owns Gaussians [o * shard_rows, (o+1) * shard_rows), shard_rows % 128 == 0): the reduce-scatter half of the
+	 * gradient exchange rides inside the preprocess-backward kernel.  scatter_bases: DEVICE array [world] of peer-mapped
+	 * staging base pointers (b200gs_gather_reduce_f32 describes the layout).  dL_dmeans2D stays local. */
+	void* const* scatter_bases;
+	int64_t scatter_shard_rows;
+	int32_t scatter_rank, scatter_world;
+	/* accumulate != 0: the six parameter-gradient arrays receive (their current contents + this view's gradient) instead of
+	 * being overwritten -- several views per optimizer step (image-parallel training with more views than ranks).  With
+	 * scatter_bases set, the sum of the local arrays and this view's gradient is what gets pushed (the local arrays
+	 * themselves are left alone): accumulate locally for all but the rank's last view, push on the last one.
+	 * 8-byte padding keeps the struct size a multiple of 8. */
+	int32_t accumulate;
+	int32_t reserved_;
 } b200gs_grads_t;
 
 int b200gs_version(void);

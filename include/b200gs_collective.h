@@ -28,6 +28,20 @@ size_t b200gs_allreduce_flag_words(int32_t world);
 int b200gs_allreduce_sum_f32(void* const* buffers_dev, void* const* flags_dev, void* multicast_ptr, int64_t offset_floats,
                              int64_t n_floats, int32_t rank, int32_t world, void* stream);
 
+/* Second half of the fused gradient exchange.  The first half happens inside b200gs_backward (b200gs_grads_t.scatter_*):
+ * every rank s has pushed its gradient rows for the Gaussians owned by rank o into o's staging buffer,
+ *     staging_o[s][c * Ps + li * w + k]   (floats; s = source rank, Ps = shard_rows, li = row within the shard,
+ *                                          (c, w) = segment offset / width in floats per Gaussian: xyz (0,3), shs (3,48),
+ *                                          opacity (51,1), scaling (52,3), rotation (55,4), feature (59,3); 64 * Ps floats per source).
+ * This call: barrier (all pushes have landed), rank r sums its shard over the sources in rank order (bit-identical
+ * result everywhere), writes the 62 reduced floats per Gaussian into EVERY rank's fused gradient buffer
+ *     out_r[c * Pp + (o * Ps + li) * w + k],  Pp = world * Ps
+ * over NVLink, barrier.  Same result as an all-reduce of the fused buffer, but the wire carries each byte once per
+ * direction and half of it is hidden under the backward kernel.  `flags` as for b200gs_allreduce_sum_f32. */
+int b200gs_gather_reduce_f32(void* const* staging_dev, void* const* out_dev, void* const* flags_dev, int64_t shard_rows,
+                             int32_t rank, int32_t world, int32_t chained /* != 0: the previous operation on `stream` is
+                             b200gs_backward (the kernel may then be launched programmatically behind it) */, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,7 +54,9 @@ class Grads(C.Structure):
     _fields_ = [("dL_dmeans3D", C.c_void_p), ("dL_dmeans2D", C.c_void_p), ("dL_dshs", C.c_void_p),
                 ("dL_dcolors", C.c_void_p), ("dL_dopacities", C.c_void_p), ("dL_dscales", C.c_void_p),
                 ("dL_drotations", C.c_void_p), ("dL_dcov3D", C.c_void_p), ("dL_dfeatures", C.c_void_p),
-                ("dL_dshs_language", C.c_void_p), ("scratch", C.c_void_p)]
+                ("dL_dshs_language", C.c_void_p), ("scratch", C.c_void_p),
+                ("scatter_bases", C.c_void_p), ("scatter_shard_rows", C.c_int64), ("scatter_rank", C.c_int32),
+                ("scatter_world", C.c_int32), ("accumulate", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class HParams(C.Structure):  # include/b200gs_train.h: b200gs_hparams_t (64 bytes, lives in device memory)
@@ -77,7 +79,7 @@ class ParamState(C.Structure):  # b200gs_param_state_t
 
 TRAIN_EXPORTS = ["b200gs_param_step", "b200gs_photometric_loss", "b200gs_photometric_scratch_bytes",
                  "b200gs_depth_pearson_loss", "b200gs_hparams_advance", "b200gs_loss_accum_doubles"]
-COLLECTIVE_EXPORTS = ["b200gs_allreduce_sum_f32", "b200gs_allreduce_flag_words"]
+COLLECTIVE_EXPORTS = ["b200gs_allreduce_sum_f32", "b200gs_allreduce_flag_words", "b200gs_gather_reduce_f32"]
 
 EXPORTS = [
     "b200gs_version", "b200gs_last_error", "b200gs_geom_bytes", "b200gs_image_bytes", "b200gs_binning_bytes",
@@ -131,6 +133,7 @@ def _load():
     lib.b200gs_allreduce_flag_words.argtypes = [C.c_int32]
     lib.b200gs_allreduce_flag_words.restype = C.c_size_t
     lib.b200gs_allreduce_sum_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
+    lib.b200gs_gather_reduce_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     assert C.sizeof(HParams) == 64
     sizes = (C.c_int64 * 6)()
     lib.b200gs_abi_sizes(sizes)

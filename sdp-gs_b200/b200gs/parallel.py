@@ -80,6 +80,23 @@ class _SymmetricBuffer:
                                            C.c_void_p(self.multicast) if self.multicast else None, C.c_int64(offset_floats),
                                            C.c_int64(n_floats), self.rank, self.world, stream))
 
+    def add_staging(self, n_floats, device):
+        """Second symmetric allocation: the per-source staging block the backward kernels of all ranks push into."""
+        import torch.distributed._symmetric_memory as symm
+        self.staging = symm.empty(n_floats, dtype=torch.float32, device=device)
+        self.staging.zero_()
+        self.shdl = symm.rendezvous(self.staging, dist.group.WORLD)
+        torch.cuda.synchronize(device)
+        dist.barrier()
+
+    def gather_reduce(self, shard_rows, chained):
+        import ctypes as C
+        from ._lib import check, lib
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        check(lib.b200gs_gather_reduce_f32(C.c_void_p(int(self.shdl.buffer_ptrs_dev)), C.c_void_p(int(self.hdl.buffer_ptrs_dev)),
+                                           C.c_void_p(int(self.fhdl.buffer_ptrs_dev)), C.c_int64(shard_rows), self.rank, self.world,
+                                           1 if chained else 0, stream))
+
 
 class FusedGradBuffer:
     """One flat f32 allocation of P*64 floats holding every per-Gaussian quantity of an image-parallel
@@ -90,17 +107,25 @@ class FusedGradBuffer:
     def __init__(self, P, device, sh_coeffs=16, symmetric=None):
         assert sh_coeffs == 16, "segment table assumes max_sh_degree = 3 (arguments/__init__.py:49)"
         self.P = P
-        Pp = self.Pp = (P + 3) // 4 * 4  # segment stride: every segment starts 16-byte aligned whatever P is
+        rank, n = world()
+        # shard of the fused exchange: rank o owns Gaussians [o * Ps, (o+1) * Ps), Ps a multiple of the 128-Gaussian tile
+        self.shard_rows = Ps = ((P + n - 1) // n + 127) // 128 * 128
         self.flat = None
         self._symm = None
-        rank, n = world()
+        self.fused_exchange = False
         mode = os.environ.get("B200GS_ALLREDUCE", "auto")
         if symmetric is None:
             symmetric = n > 1 and torch.device(device).type == "cuda" and mode != "nccl"
+        # segment stride: every segment starts 16-byte aligned whatever P is; n whole shards when the exchange is sharded
+        Pp = self.Pp = n * Ps if (symmetric and mode in ("auto", "fused")) else (P + 3) // 4 * 4
         if symmetric:
             self._symm = _SymmetricBuffer.create(Pp * FUSED_WIDTH, device, mode)
             if self._symm is not None:
                 self.flat = self._symm.tensor
+                if mode in ("auto", "fused"):
+                    # default exchange: reduce-scatter pushed by the backward kernel itself, gather by b200gs_gather_reduce_f32
+                    self._symm.add_staging(Pp * FUSED_WIDTH, device)
+                    self.fused_exchange = True
         if self.flat is None:
             self.flat = torch.zeros((Pp * FUSED_WIDTH,), dtype=torch.float32, device=device)
         self.max_radii2D = torch.zeros((P,), dtype=torch.int32, device=device)
@@ -117,6 +142,18 @@ class FusedGradBuffer:
     def zero_(self):
         self.flat.zero_()
         self.max_radii2D.zero_()
+
+    def scatter_descriptor(self):
+        """(device array of staging base pointers, shard rows, rank, world) for RasterSession(grad_scatter=...), or None
+        when the fused exchange is not available (single GPU, no symmetric memory, B200GS_ALLREDUCE=p2p|nccl)."""
+        if not self.fused_exchange:
+            return None
+        return (int(self._symm.shdl.buffer_ptrs_dev), self.shard_rows, self._symm.rank, self._symm.world)
+
+    def gather_reduce(self, chained=True):
+        """Second half of the fused exchange (the first half ran inside the rasterizer backward): afterwards every rank's
+        parameter-gradient segments hold the sum over ranks, bit-identical everywhere."""
+        self._symm.gather_reduce(self.shard_rows, chained)
 
     def add_statistics(self, viewspace_grad, radii):
         """Densification statistics of one rendered view (train.py:218-221, scene/gaussian_model.py:610-612)."""

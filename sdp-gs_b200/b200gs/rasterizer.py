@@ -354,7 +354,7 @@ class RasterSession:
 
     def __init__(self, raster_settings, *, means3D, opacities, shs=None, colors_precomp=None, scales=None,
                  rotations=None, cov3D_precomp=None, shs_language=None, language_feature_precomp=None,
-                 extended=False, capacity, grads_out=None, with_backward=True):
+                 extended=False, capacity, grads_out=None, with_backward=True, grad_scatter=None):
         rs = raster_settings
         self.rs, self.extended, self.capacity = rs, bool(extended), int(capacity)
         dev = means3D.device
@@ -415,6 +415,8 @@ class RasterSession:
             gr.dL_dmeans3D, gr.dL_dmeans2D, gr.dL_dshs, gr.dL_dcolors = _ptr(G["means3D"]), _ptr(G["means2D"]), _ptr(G["shs"]), _ptr(G["colors_precomp"])
             gr.dL_dopacities, gr.dL_dscales, gr.dL_drotations, gr.dL_dcov3D = _ptr(G["opacities"]), _ptr(G["scales"]), _ptr(G["rotations"]), _ptr(G["cov3D"])
             gr.dL_dfeatures, gr.dL_dshs_language, gr.scratch = _ptr(G["features"]), _ptr(G["shs_language"]), self.scratch.data_ptr()
+            if grad_scatter is not None:  # image-parallel training: parameter gradients are pushed to the owning ranks (parallel.FusedGradBuffer)
+                gr.scatter_bases, gr.scatter_shard_rows, gr.scatter_rank, gr.scatter_world = grad_scatter
             self.cot = dict(color=torch.zeros((3, H, W), **f32))
             go_ = self.go = GradOutputs()
             go_.dL_dcolor = self.cot["color"].data_ptr()

@@ -89,11 +89,13 @@ class GaussianTrainer:
         grads_out = dict(means3D=self.bucket.segment("xyz"), shs=self.bucket.segment("shs"), opacities=self.bucket.segment("opacity"),
                          scales=self.bucket.segment("scaling"), rotations=self.bucket.segment("rotation"),
                          shs_language=self.bucket.segment("language_feature"), means2D=self.g_means2D)
+        self._scatter = self.bucket.scatter_descriptor()
         self.sessions = []
         for cam in self.cameras:
             s = rz.RasterSession(self.settings_fn(cam), means3D=self.raw["xyz"], opacities=self.act["opacity"],
                                  shs=self.raw["shs"].view(P, 16, 3), scales=self.act["scaling"], rotations=self.act["rotation"],
-                                 shs_language=self.raw["feature"], extended=True, capacity=self.capacity, grads_out=grads_out)
+                                 shs_language=self.raw["feature"], extended=True, capacity=self.capacity, grads_out=grads_out,
+                                 grad_scatter=self.bucket.scatter_descriptor())
             self.sessions.append(s)
         self.graphs = None
 
@@ -146,9 +148,14 @@ class GaussianTrainer:
         ps = self._param_state(None)
         check(lib.b200gs_param_step(C.byref(ps), self.hp_dev.data_ptr(), 0, rz._stream()))
 
-    def _front(self, view):
-        """render, losses (+ cotangents), rasterizer backward."""
+    def _front(self, view, accumulate=False, push=True):
+        """render, losses (+ cotangents), rasterizer backward.  `accumulate`: add to the gradients earlier views of the same
+        optimizer step left behind; `push`: (image-parallel) hand the result to the owning ranks -- False for all but the
+        rank's last view of the step."""
         s = self.sessions[view]
+        s.gr.accumulate = 1 if accumulate else 0
+        if self._scatter is not None:
+            s.gr.scatter_bases = self._scatter[0] if push else None
         s.forward()
         st = rz._stream()
         check(lib.b200gs_photometric_loss(s.color.data_ptr(), self.gt[view].data_ptr(), self.W, self.H, self.hp_dev.data_ptr(),
@@ -157,6 +164,15 @@ class GaussianTrainer:
         check(lib.b200gs_depth_pearson_loss(s.depth.data_ptr(), self.mono[view].data_ptr(), self.W * self.H, self.hp_dev.data_ptr(),
                                             self.accum[self.nacc:].data_ptr(), self.loss.data_ptr(), s.cot["depth"].data_ptr(), st))
         s.backward()
+
+    def _exchange(self):
+        """Combine the ranks' parameter gradients.  Default: the backward kernels have already pushed every gradient tile to
+        the rank that owns it (reduce-scatter inside preprocess-backward); this is the gather half.  Fallbacks: the two-shot
+        all-reduce kernel (B200GS_ALLREDUCE=p2p) or NCCL."""
+        if self.bucket.fused_exchange:
+            self.bucket.gather_reduce(chained=True)
+        else:
+            self.bucket.all_reduce()
 
     def _back(self, view):
         ps = self._param_state(view)
@@ -170,7 +186,7 @@ class GaussianTrainer:
         self.iteration += 1
         self._front(view)
         if parallel.world()[1] > 1:
-            self.bucket.all_reduce()
+            self._exchange()
         self._back(view)
 
     def capture(self):
@@ -189,7 +205,7 @@ class GaussianTrainer:
             with torch.cuda.graph(ga):
                 self._front(v)
                 if own_collective:
-                    self.bucket.all_reduce()
+                    self._exchange()
                 if world == 1 or own_collective:
                     self._back(v)
             gb = None
@@ -209,6 +225,40 @@ class GaussianTrainer:
         if gb is not None:
             self.bucket.all_reduce()
             gb.replay()
+
+    # ------------------------------------------------------------------ several views per optimizer step
+    def capture_multi(self, views):
+        """One CUDA graph for an optimizer step over `views` (this rank's share of the step's views, BASELINE.json configs[4]:
+        8 views per step split over the ranks): every view is rendered and back-propagated, gradients accumulate in the
+        kernel that produces them (b200gs_grads_t.accumulate), the last view pushes the sum to the owning ranks, then the
+        gather half of the exchange and ONE Adam step.  The densification statistics see the last view only."""
+        views = list(views)
+        world = parallel.world()[1]
+        assert world == 1 or self.bucket.fused_exchange, "multi-view steps at N > 1 need the fused exchange (symmetric memory)"
+
+        def body():
+            for i, v in enumerate(views):
+                self._front(v, accumulate=i > 0, push=i == len(views) - 1)
+            if world > 1:
+                self._exchange()
+            self._back(views[-1])
+
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            for i, v in enumerate(views):  # warm-up outside capture: front parts only (no parameter changes)
+                self._front(v, accumulate=i > 0, push=False)
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            body()
+        self.multi_graph = g
+        return self
+
+    def step_multi(self):
+        self.iteration += 1
+        self.multi_graph.replay()
 
     # ------------------------------------------------------------------ densification (host-side logic, every ~100 iterations)
     @staticmethod

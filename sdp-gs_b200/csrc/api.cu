@@ -333,6 +333,13 @@ int b200gs_backward(const b200gs_view_t* v, const b200gs_gaussians_t* g, const i
 	const int P = g->P;
 	if (P == 0) return 0;  // rasterize_points.cu:161
 	if (!radii || !grads->scratch) return fail(B200GS_E_ARG, "radii and scratch are required");
+	if (grads->scatter_bases) {
+		if (grads->scatter_world < 2 || grads->scatter_rank < 0 || grads->scatter_rank >= grads->scatter_world || grads->scatter_shard_rows <= 0 ||
+		    (grads->scatter_shard_rows & 127) || grads->scatter_shard_rows * grads->scatter_world < P)
+			return fail(B200GS_E_ARG, "bad gradient scatter descriptor (shard_rows must be a multiple of 128 and cover P)");
+		if (!g->shs || v->sh_coeffs != 16 || !g->scales || !g->rotations)
+			return fail(B200GS_E_ARG, "gradient scatter needs shs with 16 coefficients and the scales/rotations path");
+	}
 	if (!ws->binning || ws->binning_bytes < b200gs_binning_bytes(capacity)) return fail(B200GS_E_ARG, "binning workspace too small");
 	cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
 	GeomState gs = geom_from_chunk(reinterpret_cast<char*>(ws->geom), P);

@@ -96,6 +96,52 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_multimem_kernel(void* co
 	block_barrier(s_flags, rank, world, 1);
 }
 
+// Gather half of the fused gradient exchange (include/b200gs_collective.h: b200gs_gather_reduce_f32).
+template <int WORLD>
+__global__ void __launch_bounds__(AR_THREADS) gather_reduce_kernel(void* const* __restrict__ staging, void* const* __restrict__ outs,
+                                                                    void* const* __restrict__ flags, int64_t Ps, int rank)
+{
+	__shared__ void* s_flags[AR_MAX_WORLD];
+	float4* out[WORLD];
+#pragma unroll
+	for (int r = 0; r < WORLD; r++) out[r] = reinterpret_cast<float4*>(outs[r]);
+	const float4* st = reinterpret_cast<const float4*>(staging[rank]);
+	if ((int)threadIdx.x < WORLD) s_flags[threadIdx.x] = flags[threadIdx.x];
+	pdl_trigger();
+	pdl_wait();  // this rank's own pushes (the backward kernel just before) are complete
+	__syncthreads();
+	block_barrier(s_flags, rank, WORLD, 0);  // ... and so are everybody else's
+	const int64_t Pp4 = Ps * WORLD / 4, Ps4 = Ps / 4;  // Ps % 128 == 0
+	const int64_t n4 = Ps4 * 62, src_stride4 = Ps4 * 64;
+	constexpr int UNROLL = WORLD <= 2 ? 4 : 2;
+	const int64_t stride = (int64_t)gridDim.x * AR_THREADS;
+	for (int64_t i0 = (int64_t)blockIdx.x * AR_THREADS + threadIdx.x; i0 < n4; i0 += stride * UNROLL) {
+		float4 v[UNROLL][WORLD];
+#pragma unroll
+		for (int u = 0; u < UNROLL; u++) {
+			const int64_t i = i0 + u * stride;
+#pragma unroll
+			for (int r = 0; r < WORLD; r++) v[u][r] = i < n4 ? __ldcg(st + r * src_stride4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+		}
+#pragma unroll
+		for (int u = 0; u < UNROLL; u++) {
+			const int64_t i = i0 + u * stride;
+			if (i >= n4) continue;
+			float4 a = v[u][0];  // fixed-order sum: identical on every rank
+#pragma unroll
+			for (int r = 1; r < WORLD; r++) { a.x += v[u][r].x; a.y += v[u][r].y; a.z += v[u][r].z; a.w += v[u][r].w; }
+			// segment of staging index i (float4 units of one shard): c * Ps4 <= i < (c + w) * Ps4
+			const int64_t q = i / Ps4;  // == floats-per-Gaussian offset the index falls into
+			const int c = q < 3 ? 0 : (q < 51 ? 3 : (q < 52 ? 51 : (q < 55 ? 52 : (q < 59 ? 55 : 59))));
+			const int w = q < 3 ? 3 : (q < 51 ? 48 : (q < 52 ? 1 : (q < 55 ? 3 : (q < 59 ? 4 : 3))));
+			const int64_t o = (int64_t)c * Pp4 + (int64_t)rank * Ps4 * w + (i - (int64_t)c * Ps4);
+#pragma unroll
+			for (int r = 0; r < WORLD; r++) __stcg(out[r] + o, a);
+		}
+	}
+	block_barrier(s_flags, rank, WORLD, 1);  // every shard has landed everywhere
+}
+
 int ar_blocks() {
 	static int v = -1;
 	if (v < 0) {
@@ -135,6 +181,28 @@ int b200gs_allreduce_sum_f32(void* const* buffers_dev, void* const* flags_dev, v
 	}
 	count_launch();
 	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return train_fail(B200GS_E_CUDA, cudaGetErrorString(e));
+	return 0;
+}
+
+int b200gs_gather_reduce_f32(void* const* staging_dev, void* const* out_dev, void* const* flags_dev, int64_t shard_rows,
+                             int32_t rank, int32_t world, int32_t chained, void* stream_) {
+	if (!staging_dev || !out_dev || !flags_dev || world < 2 || world > AR_MAX_WORLD || rank < 0 || rank >= world || shard_rows <= 0 ||
+	    (shard_rows & 127))
+		return train_fail(B200GS_E_ARG, "gather_reduce_f32: bad arguments (2 <= world <= 8, shard_rows a positive multiple of 128)");
+	cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+	cudaError_t e;
+	switch (world) {
+	case 2: e = launch_impl(chained ? PDL_TRAIN : 0u, gather_reduce_kernel<2>, dim3(ar_blocks()), dim3(AR_THREADS), stream, staging_dev, out_dev, flags_dev, shard_rows, rank); break;
+	case 3: e = launch_impl(chained ? PDL_TRAIN : 0u, gather_reduce_kernel<3>, dim3(ar_blocks()), dim3(AR_THREADS), stream, staging_dev, out_dev, flags_dev, shard_rows, rank); break;
+	case 4: e = launch_impl(chained ? PDL_TRAIN : 0u, gather_reduce_kernel<4>, dim3(ar_blocks()), dim3(AR_THREADS), stream, staging_dev, out_dev, flags_dev, shard_rows, rank); break;
+	case 5: e = launch_impl(chained ? PDL_TRAIN : 0u, gather_reduce_kernel<5>, dim3(ar_blocks()), dim3(AR_THREADS), stream, staging_dev, out_dev, flags_dev, shard_rows, rank); break;
+	case 6: e = launch_impl(chained ? PDL_TRAIN : 0u, gather_reduce_kernel<6>, dim3(ar_blocks()), dim3(AR_THREADS), stream, staging_dev, out_dev, flags_dev, shard_rows, rank); break;
+	case 7: e = launch_impl(chained ? PDL_TRAIN : 0u, gather_reduce_kernel<7>, dim3(ar_blocks()), dim3(AR_THREADS), stream, staging_dev, out_dev, flags_dev, shard_rows, rank); break;
+	default: e = launch_impl(chained ? PDL_TRAIN : 0u, gather_reduce_kernel<8>, dim3(ar_blocks()), dim3(AR_THREADS), stream, staging_dev, out_dev, flags_dev, shard_rows, rank); break;
+	}
+	count_launch();
+	if (e == cudaSuccess) e = cudaGetLastError();
 	if (e != cudaSuccess) return train_fail(B200GS_E_CUDA, cudaGetErrorString(e));
 	return 0;
 }

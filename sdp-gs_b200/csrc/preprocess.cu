@@ -382,7 +382,8 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_backward_kernel(
 	float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dshs,
 	float* __restrict__ dL_dcolors, float* __restrict__ dL_dopac, float* __restrict__ dL_dscales,
 	float* __restrict__ dL_drots, float* __restrict__ dL_dcov3D, float* __restrict__ dL_dfeat,
-	float* __restrict__ dL_dshs_lang, int tma_ok)
+	float* __restrict__ dL_dshs_lang, int tma_ok, void* const* __restrict__ scatter_bases, long long scatter_Ps, int scatter_rank,
+	int accumulate)
 {
 	// inputs staged as in the forward; the same buffers are reused for the outgoing gradients (a thread only ever
 	// touches its own row), which leave as contiguous bulk stores instead of 12/24/192-byte strided scalar stores
@@ -696,9 +697,29 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_backward_kernel(
 			for (int i = 48; i < 3 * M; i++) row[i] = 0.f;
 		}
 	}
+	// Image-parallel training: the parameter gradients of this 128-Gaussian tile go straight into the staging buffer of
+	// the rank that owns the tile (plain 16-byte stores over NVLink; layout in include/b200gs_collective.h), so the
+	// reduce-scatter half of the gradient exchange costs no kernel of its own.
+	float* fb = nullptr;    // owner's staging block for this source rank
+	size_t li0 = 0;         // first row of the tile inside the owner's shard
+	if (scatter_bases != nullptr) {
+		const size_t Ps = (size_t)scatter_Ps;
+		const size_t o = base / Ps;
+		li0 = base - o * Ps;
+		fb = reinterpret_cast<float*>(scatter_bases[o]) + (size_t)scatter_rank * Ps * 64;
+	}
+	if (valid && accumulate) {  // several views per optimizer step: add what the earlier views left in the local arrays
+		if (dL_dopac) o_op += dL_dopac[idx];
+		if (dL_drots) { const float4 t = reinterpret_cast<const float4*>(dL_drots)[idx]; o_rot.x += t.x; o_rot.y += t.y; o_rot.z += t.z; o_rot.w += t.w; }
+	}
 	if (valid) {
-		if (dL_dopac) dL_dopac[idx] = o_op;
-		if (dL_drots) reinterpret_cast<float4*>(dL_drots)[idx] = o_rot;
+		if (fb) {
+			fb[51 * (size_t)scatter_Ps + li0 + li] = o_op;
+			reinterpret_cast<float4*>(fb + 55 * (size_t)scatter_Ps)[li0 + li] = o_rot;
+		} else {
+			if (dL_dopac) dL_dopac[idx] = o_op;
+			if (dL_drots) reinterpret_cast<float4*>(dL_drots)[idx] = o_rot;
+		}
 	}
 	tma_store_fence();
 	__syncthreads();
@@ -711,14 +732,41 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_backward_kernel(
 			for (int i = li; i < cnt * floats_per_item; i += PRE_THREADS) g[i] = src[i];
 		}
 	};
-	put(dL_dmeans3D, s_means, 3);
+	auto push = [&](int seg, const float* src, int floats_per_item) {  // rows li0.. of segment `seg` in the owner's staging block
+		float* g = fb + (size_t)seg * (size_t)scatter_Ps + li0 * floats_per_item;  // 16-byte aligned: Ps and li0 are multiples of 128
+		const int n = cnt * floats_per_item;
+		for (int i = li; i < n / 4; i += PRE_THREADS) reinterpret_cast<float4*>(g)[i] = reinterpret_cast<const float4*>(src)[i];
+		for (int i = (n & ~3) + li; i < n; i += PRE_THREADS) g[i] = src[i];
+	};
+	if (accumulate) {
+		auto add_local = [&](const float* local, float* stage, int floats_per_item) {
+			if (local == nullptr) return;
+			const float* g = local + base * floats_per_item;
+			for (int i = li; i < cnt * floats_per_item; i += PRE_THREADS) stage[i] += g[i];
+		};
+		add_local(dL_dmeans3D, s_means, 3);
+		add_local(dL_dfeat, s_feat, 3);
+		add_local(dL_dshs_lang, s_feat, 3);
+		if (cov3D_precomp == nullptr) add_local(dL_dscales, s_geo, 3);
+		if (sh_staged) add_local(dL_dshs, s_sh, 3 * M);
+		tma_store_fence();
+		__syncthreads();
+	}
 	put(dL_dmeans2D, s_o2, 3);
 	put(dL_dcolors, s_oc, 3);
-	put(dL_dfeat, s_feat, 3);
-	put(dL_dshs_lang, s_feat, 3);
 	if (cov3D_precomp != nullptr) put(dL_dcov3D, s_geo, 6);
-	else put(dL_dscales, s_geo, 3);
-	if (sh_staged) put(dL_dshs, s_sh, 3 * M);
+	if (fb) {
+		push(0, s_means, 3);
+		if (sh_staged && M == 16) push(3, s_sh, 48);
+		if (cov3D_precomp == nullptr) push(52, s_geo, 3);
+		if (dL_dfeat != nullptr || dL_dshs_lang != nullptr) push(59, s_feat, 3);
+	} else {
+		put(dL_dmeans3D, s_means, 3);
+		put(dL_dfeat, s_feat, 3);
+		put(dL_dshs_lang, s_feat, 3);
+		if (cov3D_precomp == nullptr) put(dL_dscales, s_geo, 3);
+		if (sh_staged) put(dL_dshs, s_sh, 3 * M);
+	}
 	if (full && li == 0) { tma_store_commit(); tma_store_wait_read(); }
 }
 
@@ -757,7 +805,8 @@ void launch_preprocess_backward(const b200gs_view_t& v, const b200gs_gaussians_t
 		g.cov3D_precomp, g.language_feature_precomp, g.shs_language, g.confidence, v.viewmatrix, v.projmatrix,
 		v.campos, focal_x, focal_y, v.tan_fovx, v.tan_fovy, v.extended, reinterpret_cast<const float4*>(grec),
 		gr.dL_dmeans3D, gr.dL_dmeans2D, gr.dL_dshs, gr.dL_dcolors, gr.dL_dopacities, gr.dL_dscales,
-		gr.dL_drotations, gr.dL_dcov3D, gr.dL_dfeatures, gr.dL_dshs_language, tma_ok);
+		gr.dL_drotations, gr.dL_dcov3D, gr.dL_dfeatures, gr.dL_dshs_language, tma_ok, gr.scatter_bases,
+		(long long)gr.scatter_shard_rows, (int)gr.scatter_rank, (int)gr.accumulate);
 	count_launch();
 }
 

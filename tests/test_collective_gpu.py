@@ -40,3 +40,20 @@ def test_allreduce_matches_nccl_on_two_gpus():
     assert len(lines) >= 2, out[-2000:]
     for l in lines:
         assert "max|err|=0.000e+00" in l and "stats untouched=True" in l and "identical on all ranks=True" in l, l
+
+
+@pytest.mark.gpu
+def test_fused_gradient_exchange_on_two_gpus():
+    """reduce-scatter inside the preprocess-backward kernel + b200gs_gather_reduce_f32 == NCCL sum of the ranks' local gradients
+    (fp32 reassociation only), every word of the result written, bit-identical on both ranks."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29534", os.path.join(helpers.ROOT, "tools", "check_exchange.py"), "--P", "30000", "--iters", "5"],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env).stdout
+    lines = [l for l in out.splitlines() if l.startswith("EXCHANGE")]
+    assert len(lines) == 1, out[-3000:]
+    m = re.search(r"max rel err vs NCCL sum=([0-9.e+-]+)", lines[0])
+    assert m and float(m.group(1)) <= 1e-5, lines[0]
+    assert "nan_left=False" in lines[0] and "identical on all ranks=True" in lines[0], lines[0]
