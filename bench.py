@@ -614,7 +614,8 @@ def train_b200gs(args, wl, capacity, rank, world, flush):
         assert ov == 0, "binning capacity overflow in the training loop"
     ms_it = ms / args.steps
     return dict(iters_per_s=world * 1000.0 / ms_it, ms_per_iter=ms_it, what=TRAIN_WHAT + ", whole iteration = one CUDA-graph replay"
-                + (" + one NCCL all-reduce" if world > 1 else ""), last_loss=loss[0])
+                + ((" (gradient exchange inside the graph: reduce-scatter pushed by the backward kernel + gather kernel)" if tr.bucket.fused_exchange
+                    else " + one all-reduce") if world > 1 else ""), last_loss=loss[0])
 
 
 def train_reference(args, wl, binning_bytes, flush):

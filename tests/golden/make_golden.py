@@ -33,6 +33,9 @@ def pack_calls(inp, base, cot):
     """Extended outputs/gradients via the vanilla reference kernel (see module docstring)."""
     from oracle import ref_cuda as ref
     P = inp["means3D"].shape[0]
+    conf = inp.get("confidence")
+    if conf is not None:  # effective opacity o * conf (Appendix D); dL/do is scaled back below
+        inp = dict(inp, opacities=(inp["opacities"] * conf.reshape(inp["opacities"].shape)).astype(np.float32))
     z = base["depths"].astype(np.float32)
     f = inp["features"]
     zero3 = np.zeros(3, np.float32)
@@ -54,16 +57,19 @@ def pack_calls(inp, base, cot):
     g = base["grads"]
     tot = {}
     for k in ("means3D", "means2D", "opacities", "scales", "rotations"):
-        tot[k] = g[k] + grads[0][k] + grads[1][k]
+        extra = grads[0][k] + grads[1][k]
+        if k == "opacities" and conf is not None:  # base["grads"] already carries the factor (helpers.run_reference)
+            extra = (extra.reshape(-1) * conf.reshape(-1)).astype(np.float32).reshape(extra.shape)
+        tot[k] = g[k] + extra
     tot["means3D"] = tot["means3D"] + dz[:, None] * np.array([view[2], view[6], view[10]], np.float32)[None, :]
     tot["shs"] = g["shs"]
     tot["features"] = dfeat
     return dict(depth=depth, alpha=alpha, feature=feature, dz=dz, grads=tot)
 
 
-def main(outdir):
+def main(outdir, only=None):
     os.makedirs(outdir, exist_ok=True)
-    for name in CASES:
+    for name in (only or CASES):
         inp = case_inputs(name)
         cot = case_cotangents(inp)
         base = run_reference(inp, backward=True, cot=cot)
@@ -84,6 +90,8 @@ def main(outdir):
         np.savez_compressed(path, **arrays)
         print(name, "P", inp["means3D"].shape[0], "L", base["num_rendered"], os.path.getsize(path), "bytes")
 
+    if only:
+        return
     # config-1 shape: digests only
     from b200gs import synthetic as syn
     sc = syn.make_config("llff_fern_3view")
@@ -105,4 +113,4 @@ def main(outdir):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "_new"))
+    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "_new"), only=sys.argv[2:] or None)

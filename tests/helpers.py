@@ -33,6 +33,9 @@ CASES = {
     "tiny_sh0_mod": dict(config="tiny", view=1, extended=False, sh_degree=0, bg=(0.0, 0.0, 0.0), scale_modifier=0.7,
                          opacity="init"),
     "inside_sh1": dict(config="inside", view=1, extended=False, sh_degree=1, bg=(0.0, 0.0, 0.0)),
+    # D4: per-Gaussian confidence != 1 multiplies the opacity; pinned against the reference kernels run
+    # with opacities * confidence (and dL/dopacity scaled by the confidence)
+    "tiny_sh3_ext_conf": dict(config="tiny", view=1, extended=True, sh_degree=3, bg=(0.1, 0.0, 0.3), confidence=True),
 }
 # cases the reference CUDA code can run directly (vanilla outputs); extended ones are cross-checked by channel packing
 GRAD_KEYS = ("means3D", "means2D", "opacities", "shs", "colors_precomp", "scales", "rotations", "cov3D")
@@ -205,6 +208,9 @@ def run_product(inp, backward=True, cot=None, dev="cuda"):
 def run_reference(inp, backward=True, cot=None):
     """The unmodified reference kernels: vanilla outputs only (color, radii, intermediates, vanilla grads)."""
     from oracle import ref_cuda as ref
+    conf = inp.get("confidence")
+    if conf is not None:  # the reference has no confidence input: it multiplies the opacity (Appendix D), so feed the product
+        inp = dict(inp, opacities=(inp["opacities"] * conf.reshape(inp["opacities"].shape)).astype(np.float32), confidence=None)
     s = ref.forward(inp["means3D"], inp["opacities"], inp["cam"], inp["bg"], shs=inp["shs"],
                     colors_precomp=inp["colors_precomp"], scales=inp["scales"], rotations=inp["rotations"],
                     cov3D_precomp=inp["cov3D_precomp"], sh_degree=inp["sh_degree"], scale_modifier=inp["scale_modifier"])
@@ -222,6 +228,8 @@ def run_reference(inp, backward=True, cot=None):
         res["grads"] = dict(means3D=g["means3D"], means2D=g["means2D"], opacities=g["opacities"], shs=g["shs"],
                             colors_precomp=g["colors"], scales=g["scales"], rotations=g["rotations"], cov3D=g["cov3D"],
                             conic=g["conic"])
+        if conf is not None:  # d(o * conf)/do
+            res["grads"]["opacities"] = (res["grads"]["opacities"].reshape(-1) * conf.reshape(-1)).astype(np.float32).reshape(g["opacities"].shape)
     res["_state"] = s
     return res
 
