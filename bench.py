@@ -647,7 +647,7 @@ def train_reference(args, wl, binning_bytes, flush):
         state["it"] += 1
         vi = i % nviews
         c_rgb, c_pack = cfgs[vi]
-        tt.set_xyz_lr(opt, expon_lr(state["it"], hp["position_lr_init"], hp["position_lr_final"], lr_delay_mult=hp["position_lr_delay_mult"],
+        tt.set_xyz_lr(opt, expon_lr(state["it"] - 1, hp["position_lr_init"], hp["position_lr_final"], lr_delay_mult=hp["position_lr_delay_mult"],
                                     max_steps=hp["position_lr_max_steps"]))
         a = tt.activate(leaf)
         means2D = torch.zeros((P, 3), device=dev, requires_grad=True)

@@ -63,8 +63,10 @@ typedef struct b200gs_param_state {
 int b200gs_param_step(const b200gs_param_state_t* s, const b200gs_hparams_t* hp_device, int32_t update, void* stream);
 
 /* End of an iteration: step += 1 and lr_xyz = the exponential position schedule of utils/general_utils.py:
- * get_expon_lr_func(lr_init, lr_final, lr_delay_steps = 0, lr_delay_mult, max_steps) evaluated at the new step
- * (scene/gaussian_model.py:276-285), on the device, so that a captured step never waits for the host. */
+ * get_expon_lr_func(lr_init, lr_final, lr_delay_steps = 0, lr_delay_mult, max_steps) (scene/gaussian_model.py:276-285)
+ * evaluated at the iteration just finished -- the reference calls update_learning_rate(iteration) after
+ * optimizer.step() (train.py:230-233), so Adam step t runs at the rate of iteration t-1 -- on the device, so that
+ * a captured step never waits for the host. */
 int b200gs_hparams_advance(b200gs_hparams_t* hp_device, float lr_init, float lr_final, float lr_delay_mult,
                            float max_steps, void* stream);
 
@@ -84,6 +86,14 @@ size_t b200gs_loss_accum_doubles(void);
 int b200gs_depth_pearson_loss(const float* depth, const float* depth_mono, int32_t n,
                               const b200gs_hparams_t* hp_device, double* accum, double* loss_out,
                               float* dL_ddepth, void* stream);
+
+/* Exact 3 nearest neighbours of every point (self excluded): what the proximity densification of SDP-GS reads from
+ * its simple_knn fork (`dist, nearest_indices = distCUDA2(xyz)`, scene/gaussian_model.py:513-516; the extension is not
+ * vendored under /root/reference).  mean_dist2[i] = mean of the three squared distances (simple_knn's
+ * definition), indices[i] = the neighbours in order of increasing distance (ties: lower index first).
+ * Tiled brute force, O(P^2 / 1024) shared-memory passes: meant for the few-shot regime (P ~ 1e5) in which proximity()
+ * runs (iteration < 2000). */
+int b200gs_knn3(int32_t P, const float* xyz, float* mean_dist2, int32_t* indices, void* stream);
 
 #ifdef __cplusplus
 }

@@ -241,11 +241,36 @@ class DensifyModel:
         sel = torch.logical_and(sel, torch.max(self.get_scaling, dim=1).values <= self.percent_dense * scene_extent)
         self.densification_postfix({k: self.p[k][sel] for k in self.NAMES})
 
+    @staticmethod
+    def dist_knn3(xyz):
+        """distCUDA2 of the SDP-GS simple_knn fork restated with torch: mean squared distance to the 3 nearest neighbours (self
+        excluded) and their indices.  (simple_knn.cu of graphdeco-inria/simple-knn: boxMeanDist, K = 3; the fork adds the indices.)"""
+        x = xyz.detach().double()
+        d = ((x[:, None, :] - x[None, :, :]) ** 2).sum(-1)
+        d.fill_diagonal_(float("inf"))
+        val, idx = torch.topk(d, 3, dim=1, largest=False, sorted=True)
+        return val.mean(dim=1).float(), idx
+
+    def proximity(self, scene_extent, N=3):
+        """scene/gaussian_model.py:513-533"""
+        dist, nearest = self.dist_knn3(self.p["xyz"])
+        sel = torch.logical_and(dist > (5. * scene_extent), torch.max(self.get_scaling, dim=1).values > scene_extent)
+        new_indices = nearest[sel].reshape(-1).long()
+        source_xyz = self.p["xyz"][sel].repeat(1, N, 1).reshape(-1, 3)
+        target_xyz = self.p["xyz"][new_indices]
+        rot = torch.zeros_like(self.p["rotation"][new_indices])
+        rot[:, 0] = 1
+        self.densification_postfix(dict(xyz=(source_xyz + target_xyz) / 2, scaling=self.p["scaling"][new_indices], rotation=rot,
+                                        f_dc=torch.zeros_like(self.p["f_dc"][new_indices]), f_rest=torch.zeros_like(self.p["f_rest"][new_indices]),
+                                        opacity=self.p["opacity"][new_indices], feature=self.p["feature"][new_indices]))
+
     def densify_and_prune(self, max_grad, min_opacity, extent, max_screen_size, it, generator=None):
         grads = self.xyz_gradient_accum / self.denom
         grads[grads.isnan()] = 0.0
         self.densify_and_clone(grads, max_grad, extent)
         self.densify_and_split(grads, max_grad, extent, it, generator=generator)
+        if it < 2000:
+            self.proximity(extent)
         prune_mask = (self.get_opacity < min_opacity).squeeze()
         if max_screen_size:
             big_vs = self.max_radii2D > max_screen_size

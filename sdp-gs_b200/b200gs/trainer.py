@@ -33,7 +33,7 @@ from .schedule import DEFAULTS, expon_lr  # noqa: E402,F401  (pure Python: impor
 
 class GaussianTrainer:
     def __init__(self, *, xyz, shs, opacity_raw, scaling_raw, rotation_raw, feature, cameras, gt_images, depth_mono,
-                 device, capacity, sh_degree=3, background=None, hparams=None, settings_fn=None):
+                 device, capacity, sh_degree=3, active_sh_degree=None, background=None, hparams=None, settings_fn=None):
         dev = torch.device(device)
         self.dev = dev
         f32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32) if isinstance(a, np.ndarray) else a,
@@ -44,7 +44,11 @@ class GaussianTrainer:
         self.gt = [f32(g) for g in gt_images]
         self.mono = [f32(d).reshape(-1) for d in depth_mono]
         self.bg = f32(background) if background is not None else torch.zeros(3, device=dev)
-        self.sh_degree = sh_degree
+        self.sh_degree = sh_degree  # max_sh_degree (arguments/__init__.py:49)
+        # the reference starts at degree 0 and raises it every 500 iterations (train.py:85-86, oneupSHdegree); pass
+        # active_sh_degree=0 and call oneup_sh_degree() to follow that schedule.  Default: all coefficients active.
+        self.active_sh_degree = sh_degree if active_sh_degree is None else int(active_sh_degree)
+        self._max_rendered = 0
         H, W = int(self.cameras[0].height), int(self.cameras[0].width)
         self.H, self.W = H, W
         self.hp_dev = torch.zeros((16,), dtype=torch.float32, device=dev)
@@ -104,9 +108,35 @@ class GaussianTrainer:
         from diff_gaussian_rasterization import GaussianRasterizationSettings as S
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.dev)
         return S(image_height=cam.height, image_width=cam.width, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=self.bg,
-                 scale_modifier=1.0, viewmatrix=t(cam.viewmatrix), projmatrix=t(cam.projmatrix), sh_degree=self.sh_degree,
+                 scale_modifier=1.0, viewmatrix=t(cam.viewmatrix), projmatrix=t(cam.projmatrix), sh_degree=self.active_sh_degree,
                  campos=t(cam.campos), prefiltered=False, debug=False, include_feature=True,
                  confidence=torch.ones((self.P, 1), device=self.dev))
+
+    def oneup_sh_degree(self):
+        """GaussianModel.oneupSHdegree (scene/gaussian_model.py:182-184): one more SH band takes part in rendering and
+        receives gradients.  The degree is a launch parameter of the preprocess kernels, so the per-view graphs are
+        captured again (three times in a whole run)."""
+        if self.active_sh_degree >= self.sh_degree:
+            return self.active_sh_degree
+        self.active_sh_degree += 1
+        for s in self.sessions:
+            s.v.sh_degree = self.active_sh_degree
+        if self.graphs is not None:
+            self.capture()
+        return self.active_sh_degree
+
+    def check_overflow(self):
+        """Raise when a view needed more (Gaussian, tile) instances than the binning workspaces hold (surplus instances
+        are dropped on the device and only a flag is raised there).  Synchronizes: called where the trainer synchronizes
+        anyway (loss_values, densify_and_prune).  Also tracks the largest instance count seen, which sizes the
+        workspaces after the next densification."""
+        from ._lib import B200GSError
+        for i, s in enumerate(self.sessions):
+            n, ov = s.status()
+            self._max_rendered = max(self._max_rendered, n)
+            if ov & 1:
+                raise B200GSError(f"view {i}: num_rendered={n} exceeds the binning capacity {self.capacity}; "
+                                  "images and gradients of the steps since the last check were truncated")
 
     def _xyz_schedule(self):
         hp = self.hp
@@ -120,7 +150,8 @@ class GaussianTrainer:
         if step is None:
             step = self.iteration + 1
         li, lf, dm, ms = self._xyz_schedule()
-        xyz_lr = expon_lr(step, li, lf, lr_delay_mult=dm, max_steps=ms)
+        # Adam step t uses the rate update_learning_rate(t-1) left behind (train.py:230-233; position_lr_init for t = 1)
+        xyz_lr = expon_lr(step - 1, li, lf, lr_delay_mult=dm, max_steps=ms)
         vals = [float(step), xyz_lr, hp["feature_lr"], hp["feature_lr"] / 20.0, hp["opacity_lr"], hp["scaling_lr"], hp["rotation_lr"],
                 hp["language_feature_lr"], hp["beta1"], hp["beta2"], hp["eps"], hp["lambda_dssim"], hp["depth_weight"], 0.0, 0.0, 0.0]
         self.hp_dev.copy_(torch.tensor(vals, dtype=torch.float32))  # synchronous: not on the per-step path
@@ -273,19 +304,31 @@ class GaussianTrainer:
         R[:, 2, 0] = 2 * (x * z - r_ * y); R[:, 2, 1] = 2 * (y * z + r_ * x); R[:, 2, 2] = 1 - 2 * (x * x + y * y)
         return R
 
+    def knn3(self, xyz):
+        """(mean squared distance to the 3 nearest neighbours [P], their indices [P,3]) -- distCUDA2 of the SDP-GS simple_knn fork."""
+        xyz = xyz.detach().contiguous().float()
+        P = xyz.shape[0]
+        dist = torch.empty((P,), dtype=torch.float32, device=xyz.device)
+        idx = torch.empty((P, 3), dtype=torch.int32, device=xyz.device)
+        check(lib.b200gs_knn3(P, xyz.data_ptr(), dist.data_ptr(), idx.data_ptr(), rz._stream()))
+        return dist, idx
+
     def densify_and_prune(self, max_grad, min_opacity, extent, max_screen_size, iteration=None, percent_dense=0.01,
-                          prune_from_iter=500, N=2, generator=None, recapture=True):
+                          prune_from_iter=500, N=2, generator=None, recapture=True, proximity_until_iter=2000):
         """scene/gaussian_model.py:591-608 (densify_and_clone, densify_and_split, prune) on the trainer's buffers, in
         the reference's order of operations and row order: [survivors of the old rows | clones | split copies].  New rows
         get zero Adam moments (cat_tensors_to_optimizer), all statistics are reset (densification_postfix).  Every rank of
         an image-parallel job calls this with the same arguments: the statistics are combined first, and torch.normal
         draws from `generator` (or the global CUDA generator) -- seed it identically on every rank.
-        Not reproduced: proximity() (iteration < 2000), it needs the un-vendored simple_knn kNN.
-        Buffers are re-allocated and, with `recapture`, the per-view graphs are captured again."""
+        proximity() (scene/gaussian_model.py:513-533, run while iteration < 2000): isolated, large Gaussians grow three
+        new ones half-way to their nearest neighbours; the kNN the reference takes from its un-vendored simple_knn fork is
+        b200gs_knn3 here.  Buffers are re-allocated and, with `recapture`, the per-view graphs are captured again."""
         iteration = self.iteration if iteration is None else iteration
         if parallel.world()[1] > 1:
             self.bucket.all_reduce_statistics()
         torch.cuda.synchronize(self.dev)
+        self.check_overflow()
+        P_before = self.P
         raw = {k: t.clone() for k, t in self.raw.items()}
         m = {k: t.clone() for k, t in self.m.items()}
         v = {k: t.clone() for k, t in self.v.items()}
@@ -325,6 +368,17 @@ class GaussianTrainer:
         new["scaling"] = torch.log(get_scaling()[sel].repeat(N, 1) / (0.8 * N))
         cat(new)
         prune(torch.cat((sel, torch.zeros(N * int(sel.sum()), device=self.dev, dtype=bool))))
+        # proximity
+        if iteration < proximity_until_iter and raw["xyz"].shape[0] >= 4:
+            dist, nn = self.knn3(raw["xyz"])
+            sel = torch.logical_and(dist > 5.0 * extent, torch.max(get_scaling(), dim=1).values > extent)
+            if bool(sel.any()):
+                idx = nn[sel].reshape(-1).long()
+                source = raw["xyz"][sel].repeat(1, 3, 1).reshape(-1, 3)  # the reference's own pairing (sources tiled, targets grouped)
+                rot = torch.zeros_like(raw["rotation"][idx])
+                rot[:, 0] = 1
+                cat(dict(xyz=(source + raw["xyz"][idx]) / 2, shs=torch.zeros_like(raw["shs"][idx]), opacity=raw["opacity"][idx],
+                         scaling=raw["scaling"][idx], rotation=rot, feature=raw["feature"][idx]))
         # prune (max_radii2D was reset by densification_postfix, so the screen-size test sees zeros, as in the reference)
         mask = (torch.sigmoid(raw["opacity"]) < min_opacity).squeeze()
         if max_screen_size:
@@ -332,6 +386,9 @@ class GaussianTrainer:
             big_ws = get_scaling().max(dim=1).values > 0.1 * extent
             mask = torch.logical_or(torch.logical_or(mask, big_vs), big_ws)
         prune(mask)
+        # the instance count grows with the Gaussian count: keep 1.3x the largest count seen, scaled by the growth
+        need = int(1.3 * self._max_rendered * max(1.0, raw["xyz"].shape[0] / max(P_before, 1))) + 4096
+        self.capacity = max(self.capacity, need)
         self._allocate(raw, m, v)
         self._refresh_activations()
         if recapture:
@@ -378,8 +435,9 @@ class GaussianTrainer:
                         scaling=n(self.raw["scaling"]), rotation=n(self.raw["rotation"]), feature=n(self.raw["feature"]))
 
     def loss_values(self):
-        """(total, L1, SSIM, weighted depth loss) of the last step."""
+        """(total, L1, SSIM, weighted depth loss) of the last step.  Synchronizes, and checks the binning capacity."""
         t = self.loss.cpu().numpy()
+        self.check_overflow()
         return float(t[0]), float(t[1]), float(t[2]), float(t[3])
 
     def parameters(self):

@@ -386,13 +386,53 @@ __global__ void hparams_advance_kernel(b200gs_hparams_t* hp, float lr_init, floa
 	pdl_trigger();
 	pdl_wait();
 	if (threadIdx.x != 0 || blockIdx.x != 0) return;
-	const float step = hp->step + 1.f;
-	hp->step = step;
+	// The reference calls update_learning_rate(iteration) AFTER optimizer.step() (train.py:230-233): Adam step t runs with
+	// the learning rate of iteration t-1 (position_lr_init for the first one).  The block is advanced after step `done`,
+	// so the rate it leaves for step done+1 is expon_lr(done).
+	const float done = hp->step;
+	hp->step = done + 1.f;
 	if (lr_init == 0.f && lr_final == 0.f) { hp->lr_xyz = 0.f; return; }
 	// lr_delay_steps == 0 in scene/gaussian_model.py:268-271, so delay_rate == 1 (delay_mult only matters with delay steps)
 	(void)delay_mult;
-	const double t = fmin(fmax((double)step / (double)max_steps, 0.0), 1.0);
+	const double t = fmin(fmax((double)done / (double)max_steps, 0.0), 1.0);
 	hp->lr_xyz = (float)exp(log((double)lr_init) * (1.0 - t) + log((double)lr_final) * t);
+}
+
+// Exact 3-NN, brute force over shared-memory tiles of candidates (b200gs_knn3).
+constexpr int KNN_THREADS = 256;
+constexpr int KNN_TILE = 2048;
+__global__ void __launch_bounds__(KNN_THREADS) knn3_kernel(int P, const float* __restrict__ xyz, float* __restrict__ mean_d2, int32_t* __restrict__ idx3) {
+	__shared__ float s_x[KNN_TILE], s_y[KNN_TILE], s_z[KNN_TILE];
+	const int i = blockIdx.x * KNN_THREADS + threadIdx.x;
+	const bool live = i < P;
+	const float qx = live ? xyz[3 * (size_t)i] : 0.f, qy = live ? xyz[3 * (size_t)i + 1] : 0.f, qz = live ? xyz[3 * (size_t)i + 2] : 0.f;
+	float d0 = 3.0e38f, d1 = 3.0e38f, d2 = 3.0e38f;
+	int i0 = -1, i1 = -1, i2 = -1;
+	for (int base = 0; base < P; base += KNN_TILE) {
+		const int cnt = min(KNN_TILE, P - base);
+		__syncthreads();
+		for (int j = threadIdx.x; j < cnt; j += KNN_THREADS) {
+			s_x[j] = xyz[3 * (size_t)(base + j)]; s_y[j] = xyz[3 * (size_t)(base + j) + 1]; s_z[j] = xyz[3 * (size_t)(base + j) + 2];
+		}
+		__syncthreads();
+		if (!live) continue;
+#pragma unroll 4
+		for (int j = 0; j < cnt; j++) {
+			const float dx = s_x[j] - qx, dy = s_y[j] - qy, dz = s_z[j] - qz;
+			const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));  // simple_knn: d.x*d.x + d.y*d.y + d.z*d.z, left to right
+			if (d < d2 && base + j != i) {  // candidates arrive in index order and ties do not displace: lower index first
+				if (d < d1) {
+					d2 = d1; i2 = i1;
+					if (d < d0) { d1 = d0; i1 = i0; d0 = d; i0 = base + j; }
+					else { d1 = d; i1 = base + j; }
+				} else { d2 = d; i2 = base + j; }
+			}
+		}
+	}
+	if (live) {
+		mean_d2[i] = (d0 + d1 + d2) / 3.0f;
+		idx3[3 * (size_t)i] = i0; idx3[3 * (size_t)i + 1] = i1; idx3[3 * (size_t)i + 2] = i2;
+	}
 }
 
 Window make_window() {
@@ -439,6 +479,17 @@ int b200gs_depth_pearson_loss(const float* depth, const float* depth_mono, int32
 	launch_k(PDL_TRAIN, pearson_reduce_kernel, dim3(grid), dim3(256), stream, depth, depth_mono, (int)n, accum, hp, loss_out);
 	launch_k(PDL_TRAIN, pearson_grad_kernel, dim3(grid), dim3(256), stream, depth, depth_mono, (int)n, (const double*)(accum + 16 * ACC_SLOTS + 2), dL_ddepth);
 	count_launch(2);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return train_fail(B200GS_E_CUDA, cudaGetErrorString(e));
+	return 0;
+}
+
+int b200gs_knn3(int32_t P, const float* xyz, float* mean_dist2, int32_t* indices, void* stream_) {
+	if (P < 0 || (P > 0 && (!xyz || !mean_dist2 || !indices))) return train_fail(B200GS_E_ARG, "knn3: bad arguments");
+	if (P < 4) return train_fail(B200GS_E_ARG, "knn3: at least 4 points are needed for 3 neighbours");
+	cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+	knn3_kernel<<<(P + KNN_THREADS - 1) / KNN_THREADS, KNN_THREADS, 0, stream>>>(P, xyz, mean_dist2, indices);
+	count_launch();
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return train_fail(B200GS_E_CUDA, cudaGetErrorString(e));
 	return 0;

@@ -185,7 +185,7 @@ def test_trainer_iterations_match_autograd_pipeline():
         view = (it - 1) % len(cams)
         tr.step(view)
         mine = tr.loss_values()
-        tt.set_xyz_lr(opt, expon_lr(it, hp["position_lr_init"], hp["position_lr_final"], lr_delay_mult=hp["position_lr_delay_mult"],
+        tt.set_xyz_lr(opt, expon_lr(it - 1, hp["position_lr_init"], hp["position_lr_final"], lr_delay_mult=hp["position_lr_delay_mult"],
                                     max_steps=hp["position_lr_max_steps"]))
         a = tt.activate(leaf)
         means2D = torch.zeros((P, 3), device=dev, requires_grad=True)
@@ -285,7 +285,7 @@ def test_short_fit_lands_within_a_tenth_of_a_db_of_the_reference_pipeline():
     opt = tt.make_optimizer(leaf, hp)
     for it in range(1, K + 1):
         v = (it - 1) % len(cams)
-        tt.set_xyz_lr(opt, expon_lr(it, hp["position_lr_init"], hp["position_lr_final"], lr_delay_mult=hp["position_lr_delay_mult"],
+        tt.set_xyz_lr(opt, expon_lr(it - 1, hp["position_lr_init"], hp["position_lr_final"], lr_delay_mult=hp["position_lr_delay_mult"],
                                     max_steps=hp["position_lr_max_steps"]))
         color, depth = ref_render(tt.activate(leaf), *cfgs[v])
         total, _, _, _ = tt.total_loss(color, gts[v], depth, monos[v], hp["lambda_dssim"], hp["depth_weight"])
@@ -304,6 +304,56 @@ def test_short_fit_lands_within_a_tenth_of_a_db_of_the_reference_pipeline():
     for a, b in zip(mine, ref):
         assert abs(a - b) <= 0.3, (mine, ref)
     assert min(mine) > start + 3.0  # and the fit actually went somewhere
+
+
+@gpu
+def test_knn3_and_proximity_densification():
+    """b200gs_knn3 (the distCUDA2 of the un-vendored simple_knn fork) against a torch restatement, then a densify_and_prune in
+    the regime where proximity() fires (iteration < 2000, scene/gaussian_model.py:513-533, 598-599): identical rows."""
+    from b200gs.trainer import GaussianTrainer, DEFAULTS
+    from oracle import train_torch as tt
+    dev = torch.device("cuda", 0)
+    sc, cams, gts, monos, raw = _trainer_inputs("small", dev)
+    tr = GaussianTrainer(cameras=cams, gt_images=gts, depth_mono=monos, device=dev, capacity=400_000, **raw)
+    tr.capture()
+    for it in range(4):
+        tr.step(it % len(cams))
+    torch.cuda.synchronize()
+    P = tr.P
+    dist, nn = tr.knn3(tr.raw["xyz"])
+    d_ref, nn_ref = tt.DensifyModel.dist_knn3(tr.raw["xyz"])
+    assert torch.equal(nn.long(), nn_ref)
+    assert float(((dist - d_ref).abs() / d_ref).max()) <= 1e-5
+    snap = {k: v.clone() for k, v in tr.raw.items()}
+    mom = {k: (tr.m[k].clone(), tr.v[k].clone()) for k in tr.raw}
+    accum, denom = tr.bucket.segment("xyz_gradient_accum").clone(), tr.bucket.segment("denom").clone()
+    extent = float(torch.quantile(dist, 0.7)) / 5.0  # the 30 % most isolated Gaussians qualify by distance
+    thr = float(torch.quantile((accum / denom.clamp_min(1)).squeeze(), 0.95))
+    args = dict(max_grad=thr, min_opacity=0.05, extent=extent, max_screen_size=None)
+    model = tt.DensifyModel(dict(xyz=snap["xyz"], f_dc=snap["shs"].view(P, 16, 3)[:, :1], f_rest=snap["shs"].view(P, 16, 3)[:, 1:],
+                                 opacity=snap["opacity"], scaling=snap["scaling"], rotation=snap["rotation"], feature=snap["feature"]),
+                            dict(DEFAULTS),
+                            moments=dict(xyz=mom["xyz"], f_dc=tuple(t.view(P, 16, 3)[:, :1] for t in mom["shs"]),
+                                         f_rest=tuple(t.view(P, 16, 3)[:, 1:] for t in mom["shs"]), opacity=mom["opacity"],
+                                         scaling=mom["scaling"], rotation=mom["rotation"], feature=mom["feature"]))
+    model.xyz_gradient_accum, model.denom = accum.clone(), denom.clone()
+    n_before = P
+    g1 = torch.Generator(device=dev).manual_seed(77)
+    model.densify_and_prune(it=1000, generator=g1, **args)
+    g2 = torch.Generator(device=dev).manual_seed(77)
+    newP = tr.densify_and_prune(iteration=1000, generator=g2, **args)
+    assert newP == model.p["xyz"].shape[0] and newP > n_before
+    ref = dict(xyz=model.p["xyz"], shs=torch.cat((model.p["f_dc"], model.p["f_rest"]), 1).reshape(newP, 48), opacity=model.p["opacity"],
+               scaling=model.p["scaling"], rotation=model.p["rotation"], feature=model.p["feature"])
+    for k in tr.raw:
+        assert torch.equal(tr.raw[k], ref[k].detach()), k
+    # proximity rows exist: identity rotations with zero SH are only produced there
+    prox = (tr.raw["rotation"] == torch.tensor([1.0, 0.0, 0.0, 0.0], device=dev)).all(dim=1) & (tr.raw["shs"] == 0).all(dim=1)
+    assert int(prox.sum()) > 0
+    for it in range(2):
+        tr.step(it % len(cams))
+    torch.cuda.synchronize()
+    assert np.isfinite(tr.loss_values()[0])
 
 
 @gpu
