@@ -427,6 +427,82 @@ class GaussianTrainer:
         if recapture:
             self.capture()
 
+    # group order of GaussianModel.training_setup with include_feature (scene/gaussian_model.py:228-237) and the trainer's names
+    _REF_GROUPS = (("language_feature", "feature", "language_feature_lr"), ("f_dc", "shs", "feature_lr"), ("f_rest", "shs", "feature_lr"),
+                   ("xyz", "xyz", "position_lr_init"), ("opacity", "opacity", "opacity_lr"), ("scaling", "scaling", "scaling_lr"),
+                   ("rotation", "rotation", "rotation_lr"))
+
+    def _ref_views(self, store):
+        """The trainer's flat [P,48] SH block as the reference's two leaves f_dc [P,1,3] / f_rest [P,15,3], plus the rest."""
+        P = self.P
+        sh = store["shs"].view(P, 16, 3)
+        return dict(language_feature=store["feature"], f_dc=sh[:, :1], f_rest=sh[:, 1:], xyz=store["xyz"], opacity=store["opacity"],
+                    scaling=store["scaling"], rotation=store["rotation"])
+
+    def capture_reference(self):
+        """The 15-tuple GaussianModel.capture(include_feature=True) returns (scene/gaussian_model.py:67-84) -- what train.py:212-215
+        saves as (tuple, iteration) in chkpnt*.pth -- with the optimizer state in torch.optim.Adam's own state_dict layout
+        (parameter groups in the reference's order, `step` = iterations done), so a reference process can restore() it."""
+        from torch import nn
+        raw, m, v = self._ref_views(self.raw), self._ref_views(self.m), self._ref_views(self.v)
+        hp = self.hp
+        leaves, groups = {}, []
+        for name, _, lr_key in self._REF_GROUPS:
+            leaves[name] = nn.Parameter(raw[name].detach().clone().contiguous().requires_grad_(True))
+            lr = hp[lr_key] * (hp["spatial_lr_scale"] if name == "xyz" else 1.0) / (20.0 if name == "f_rest" else 1.0)
+            groups.append({"params": [leaves[name]], "lr": lr, "name": name})
+        opt = torch.optim.Adam(groups, lr=0.0, eps=hp["eps"], betas=(hp["beta1"], hp["beta2"]))
+        for g in opt.param_groups:
+            if g["name"] == "xyz":  # the rate update_learning_rate(iteration) left behind
+                li, lf, dm, ms = self._xyz_schedule()
+                g["lr"] = expon_lr(self.iteration, li, lf, lr_delay_mult=dm, max_steps=ms)
+            p = g["params"][0]
+            opt.state[p] = {"step": torch.tensor(float(self.iteration)), "exp_avg": m[g["name"]].detach().clone().contiguous(),
+                            "exp_avg_sq": v[g["name"]].detach().clone().contiguous()}
+        return (self.active_sh_degree, leaves["xyz"], leaves["f_dc"], leaves["f_rest"], torch.empty(0), leaves["scaling"], leaves["rotation"],
+                leaves["opacity"], leaves["language_feature"], self.bucket.max_radii2D.detach().clone().float(),
+                self.bucket.segment("xyz_gradient_accum").detach().clone(), self.bucket.segment("denom").detach().clone(),
+                opt.state_dict(), float(hp["spatial_lr_scale"]), torch.ones((self.P, 1), device=self.dev))
+
+    def restore_reference(self, model_args, recapture=True):
+        """Inverse: load a capture() tuple written by the reference (15 entries with the feature head, 13 without;
+        scene/gaussian_model.py:104-143).  Adam moments are taken from its optimizer state_dict by group name."""
+        model_args = tuple(model_args)
+        if len(model_args) == 15:
+            (deg, xyz, f_dc, f_rest, _dc_lang, scaling, rotation, opacity, lang, max_radii2D, accum, denom, opt_dict, spatial, _conf) = model_args
+        elif len(model_args) == 13:
+            (deg, xyz, f_dc, f_rest, scaling, rotation, opacity, max_radii2D, accum, denom, opt_dict, spatial, _conf) = model_args
+            lang = torch.zeros((xyz.shape[0], 3))
+        else:
+            raise ValueError(f"not a GaussianModel.capture() tuple: {len(model_args)} entries")
+        to = lambda t: t.detach().to(self.dev, dtype=torch.float32)
+        P = int(xyz.shape[0])
+        raw = dict(xyz=to(xyz), shs=torch.cat((to(f_dc), to(f_rest)), dim=1).reshape(P, 48), opacity=to(opacity).reshape(P, 1),
+                   scaling=to(scaling), rotation=to(rotation), feature=to(lang))
+        names = [g["name"] for g in opt_dict["param_groups"]]
+        st = {n: opt_dict["state"].get(g["params"][0]) for n, g in zip(names, opt_dict["param_groups"])}
+        zeros = lambda k: torch.zeros_like(raw[k])
+        mom = lambda key, n: to(st[n][key]).reshape(P, -1) if st.get(n) is not None else None
+        m, v = {}, {}
+        for key, store in (("exp_avg", m), ("exp_avg_sq", v)):
+            dc, rest = mom(key, "f_dc"), mom(key, "f_rest")
+            store["shs"] = (torch.cat((dc.view(P, 1, 3), rest.view(P, 15, 3)), dim=1).reshape(P, 48) if dc is not None and rest is not None else zeros("shs"))
+            for k, n in (("xyz", "xyz"), ("opacity", "opacity"), ("scaling", "scaling"), ("rotation", "rotation"), ("feature", "language_feature")):
+                t = mom(key, n)
+                store[k] = t.reshape(raw[k].shape) if t is not None else zeros(k)
+        steps = [float(s["step"]) for s in st.values() if s is not None and "step" in s]
+        self.hp["spatial_lr_scale"] = float(spatial)
+        self.active_sh_degree = int(deg)
+        self._allocate(raw, m, v)
+        self.bucket.segment("xyz_gradient_accum").copy_(to(accum).reshape(P, 1))
+        self.bucket.segment("denom").copy_(to(denom).reshape(P, 1))
+        self.bucket.max_radii2D.copy_(max_radii2D.detach().to(self.dev).to(torch.int32))
+        self.iteration = int(max(steps)) if steps else 0
+        self.set_hparams(step=self.iteration + 1)
+        self._refresh_activations()
+        if recapture:
+            self.capture()
+
     def save_ply(self, path):
         """Point cloud in the reference's PLY layout (scene/gaussian_model.py:303-325) through b200gs.ply_io."""
         from . import ply_io

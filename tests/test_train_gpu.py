@@ -307,6 +307,56 @@ def test_short_fit_lands_within_a_tenth_of_a_db_of_the_reference_pipeline():
 
 
 @gpu
+def test_reference_checkpoint_tuple_round_trip():
+    """GaussianTrainer.capture_reference() is the 15-tuple of GaussianModel.capture(include_feature=True)
+    (scene/gaussian_model.py:67-84): field order, leaf shapes, and an optimizer state_dict that torch.optim.Adam built over
+    the reference's parameter groups (oracle/train_torch.make_optimizer) loads as is; restore_reference() brings a fresh
+    trainer to the identical state, and both continue identically."""
+    from b200gs.trainer import GaussianTrainer, DEFAULTS
+    from oracle import train_torch as tt
+    dev = torch.device("cuda", 0)
+    sc, cams, gts, monos, raw = _trainer_inputs("tiny", dev)
+    mk = lambda: GaussianTrainer(cameras=cams, gt_images=gts, depth_mono=monos, device=dev, capacity=100_000, **raw)
+    tr = mk().capture()
+    for it in range(5):
+        tr.step(it % len(cams))
+    torch.cuda.synchronize()
+    P = tr.P
+    ck = tr.capture_reference()
+    assert len(ck) == 15 and ck[0] == tr.active_sh_degree
+    assert tuple(ck[1].shape) == (P, 3) and tuple(ck[2].shape) == (P, 1, 3) and tuple(ck[3].shape) == (P, 15, 3)
+    assert ck[4].numel() == 0 and tuple(ck[5].shape) == (P, 3) and tuple(ck[6].shape) == (P, 4) and tuple(ck[7].shape) == (P, 1)
+    assert tuple(ck[8].shape) == (P, 3) and tuple(ck[9].shape) == (P,) and tuple(ck[10].shape) == (P, 1) and tuple(ck[11].shape) == (P, 1)
+    assert ck[13] == DEFAULTS["spatial_lr_scale"] and tuple(ck[14].shape) == (P, 1)
+    # a reference-side optimizer accepts the state dict (same groups, same order, same hyper-parameters)
+    leaf = dict(feature=ck[8], f_dc=ck[2], f_rest=ck[3], xyz=ck[1], opacity=ck[7], scaling=ck[5], rotation=ck[6])
+    opt = tt.make_optimizer({k: torch.nn.Parameter(v.detach().clone()) for k, v in leaf.items()}, dict(DEFAULTS))
+    assert [g["name"] for g in ck[12]["param_groups"]] == [g["name"] for g in opt.param_groups]
+    opt.load_state_dict(ck[12])
+    st = {g["name"]: opt.state[g["params"][0]] for g in opt.param_groups}
+    assert float(st["xyz"]["step"]) == 5.0 and torch.equal(st["xyz"]["exp_avg"], tr.m["xyz"])
+    assert torch.equal(st["f_rest"]["exp_avg_sq"].reshape(P, 45), tr.v["shs"].view(P, 16, 3)[:, 1:].reshape(P, 45))
+    assert opt.param_groups[3]["eps"] == 1e-15
+    # torch.save / torch.load as train.py:212-215 does, then into a fresh trainer
+    import io
+    buf = io.BytesIO()
+    torch.save((ck, tr.iteration), buf)
+    buf.seek(0)
+    loaded, it0 = torch.load(buf, weights_only=False)
+    tr2 = mk()
+    tr2.restore_reference(loaded)
+    assert tr2.iteration == it0 == 5
+    for k in tr.raw:
+        assert torch.equal(tr.raw[k], tr2.raw[k]) and torch.equal(tr.m[k], tr2.m[k]) and torch.equal(tr.v[k], tr2.v[k]), k
+    assert torch.equal(tr.bucket.segment("denom"), tr2.bucket.segment("denom"))
+    for it in range(5, 8):
+        tr.step(it % len(cams)); tr2.step(it % len(cams))
+    torch.cuda.synchronize()
+    for k in tr.raw:  # the restored trainer recomputes the position rate on the host (f64) -- last-bit differences at most
+        torch.testing.assert_close(tr.raw[k], tr2.raw[k], rtol=1e-5, atol=1e-7, msg=k)
+
+
+@gpu
 def test_knn3_and_proximity_densification():
     """b200gs_knn3 (the distCUDA2 of the un-vendored simple_knn fork) against a torch restatement, then a densify_and_prune in
     the regime where proximity() fires (iteration < 2000, scene/gaussian_model.py:513-533, 598-599): identical rows."""
