@@ -93,6 +93,13 @@ typedef struct b200gs_workspace {
 	size_t binning_bytes;
 	void* image;
 	size_t image_bytes;
+	/* persistent != 0: the caller keeps these workspaces (and b200gs_grads_t.scratch) alive across calls, initialised them
+	 * once with b200gs_workspace_init, and lets nothing else write to them.  The kernels then leave every counter,
+	 * histogram and look-back word they consumed zeroed for the next call (and the backward re-zeroes the scratch rows it
+	 * read), so no call issues a memset -- the steady state of a training loop (CUDA-graph sessions).  0: fresh or foreign
+	 * memory; every call zeroes what it needs first (the eager autograd path, which allocates per call). */
+	int32_t persistent;
+	int32_t reserved_;
 } b200gs_workspace_t;
 
 /* Cotangents of the outputs (device, CHW).  NULL == zero. */
@@ -118,7 +125,7 @@ typedef struct b200gs_grads {
 	float* dL_dcov3D;         /* [P,6]   or NULL (for cov3D_precomp) */
 	float* dL_dfeatures;      /* [P,3]   or NULL (language_feature_precomp) */
 	float* dL_dshs_language;  /* [P,3]   or NULL */
-	void* scratch;            /* P*64 bytes */
+	void* scratch;            /* P*64 bytes; with ws->persistent: all zeros on entry, all zeros again on return */
 	/* Image-parallel training (include/b200gs_collective.h): when scatter_bases != NULL the six parameter-gradient arrays
 	 * (means3D, shs [M = 16], opacities, scales, rotations, features / shs_language) are NOT written to the pointers above
 	 * but pushed, 128-Gaussian tile by tile, over NVLink into the staging buffer of the rank that owns the tile
@@ -144,6 +151,10 @@ size_t b200gs_geom_bytes(int32_t P);
 size_t b200gs_image_bytes(int32_t width, int32_t height);
 size_t b200gs_binning_bytes(int64_t capacity); /* capacity = max number of (Gaussian,tile) instances, < 2^30 */
 size_t b200gs_scratch_bytes(int32_t P);
+
+/* One-time initialisation of persistent workspaces (see b200gs_workspace_t.persistent): zeroes the geom workspace's
+ * counter region and, when `scratch` != NULL, the P*64-byte backward scratch. */
+int b200gs_workspace_init(const b200gs_workspace_t* ws, int32_t P, void* scratch, void* stream);
 
 /* Stage 1 of the forward: preprocess, depth ordering, instance count.  Needs ws->geom and
  * ws->image.  Writes out->radii.  If `num_rendered_host` != NULL the instance count is copied to

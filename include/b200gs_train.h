@@ -59,7 +59,8 @@ typedef struct b200gs_param_state {
 } b200gs_param_state_t;
 
 /* One fused launch: chain rule through the activations, Adam update, re-activation, densification statistics.
- * `update` == 0 only refreshes the activated copies from the raw parameters (no gradient needed). */
+ * `update` == 0 only refreshes the activated copies from the raw parameters (no gradient needed); 2 = densification
+ * statistics only (train.py:218-231 on a densify iteration: the parameters were just re-created, optimizer.step() is a no-op). */
 int b200gs_param_step(const b200gs_param_state_t* s, const b200gs_hparams_t* hp_device, int32_t update, void* stream);
 
 /* End of an iteration: step += 1 and lr_xyz = the exponential position schedule of utils/general_utils.py:
@@ -86,6 +87,15 @@ size_t b200gs_loss_accum_doubles(void);
 int b200gs_depth_pearson_loss(const float* depth, const float* depth_mono, int32_t n,
                               const b200gs_hparams_t* hp_device, double* accum, double* loss_out,
                               float* dL_ddepth, void* stream);
+
+/* The pseudo-view form of the same loss (train.py:138-153: a second render from an unobserved pose, supervised by a
+ * monocular depth estimate): loss_out[3] = w * (1 - pearson(depth, depth_ref)) is ADDED to loss_out[0], with
+ * w = *weight_device (loss_scale * depth_pseudo_weight, its own device word so that the ramp of train.py:150 needs no
+ * re-capture) or hp->depth_weight when weight_device is NULL; single_branch != 0 selects the single correlation
+ * (pass depth_ref = -midas), 0 the min over (depth_ref, 1 / (200 - depth_ref)) of the training views. */
+int b200gs_depth_pearson_loss_pseudo(const float* depth, const float* depth_ref, int32_t n, const b200gs_hparams_t* hp_device,
+                                     const float* weight_device, int32_t single_branch, double* accum, double* loss_out,
+                                     float* dL_ddepth, void* stream);
 
 /* Exact 3 nearest neighbours of every point (self excluded): what the proximity densification of SDP-GS reads from
  * its simple_knn fork (`dist, nearest_indices = distCUDA2(xyz)`, scene/gaussian_model.py:513-516; the extension is not

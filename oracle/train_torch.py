@@ -246,10 +246,32 @@ class DensifyModel:
         """distCUDA2 of the SDP-GS simple_knn fork restated with torch: mean squared distance to the 3 nearest neighbours (self
         excluded) and their indices.  (simple_knn.cu of graphdeco-inria/simple-knn: boxMeanDist, K = 3; the fork adds the indices.)"""
         x = xyz.detach().double()
-        d = ((x[:, None, :] - x[None, :, :]) ** 2).sum(-1)
-        d.fill_diagonal_(float("inf"))
-        val, idx = torch.topk(d, 3, dim=1, largest=False, sorted=True)
+        P = x.shape[0]
+        vals, idxs = [], []
+        for a in range(0, P, 1024):  # row blocks: the full P x P matrix does not fit for P ~ 1e5
+            d = ((x[a:a + 1024, None, :] - x[None, :, :]) ** 2).sum(-1)
+            r = torch.arange(a, min(a + 1024, P), device=x.device)
+            d[r - a, r] = float("inf")
+            val, idx = torch.topk(d, 3, dim=1, largest=False, sorted=True)
+            vals.append(val); idxs.append(idx)
+        val, idx = torch.cat(vals), torch.cat(idxs)
         return val.mean(dim=1).float(), idx
+
+    def reset_opacity(self):
+        """scene/gaussian_model.py:351-355 + replace_tensor_to_optimizer (:400-413)"""
+        from torch import nn
+        new = torch.log(torch.min(self.get_opacity, torch.ones_like(self.get_opacity) * 0.01) / (1 - torch.min(self.get_opacity, torch.ones_like(self.get_opacity) * 0.01)))
+        for group in self.optimizer.param_groups:
+            if group["name"] == "opacity":
+                stored = self.optimizer.state.get(group["params"][0], None)
+                if stored is not None:
+                    stored["exp_avg"] = torch.zeros_like(new)
+                    stored["exp_avg_sq"] = torch.zeros_like(new)
+                    del self.optimizer.state[group["params"][0]]
+                group["params"][0] = nn.Parameter(new.detach().requires_grad_(True))
+                if stored is not None:
+                    self.optimizer.state[group["params"][0]] = stored
+                self.p["opacity"] = group["params"][0]
 
     def proximity(self, scene_extent, N=3):
         """scene/gaussian_model.py:513-533"""

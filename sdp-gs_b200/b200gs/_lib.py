@@ -42,7 +42,8 @@ class Outputs(C.Structure):
 
 class Workspace(C.Structure):
     _fields_ = [("geom", C.c_void_p), ("geom_bytes", C.c_size_t), ("binning", C.c_void_p),
-                ("binning_bytes", C.c_size_t), ("image", C.c_void_p), ("image_bytes", C.c_size_t)]
+                ("binning_bytes", C.c_size_t), ("image", C.c_void_p), ("image_bytes", C.c_size_t),
+                ("persistent", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class GradOutputs(C.Structure):
@@ -78,12 +79,12 @@ class ParamState(C.Structure):  # b200gs_param_state_t
 
 
 TRAIN_EXPORTS = ["b200gs_param_step", "b200gs_photometric_loss", "b200gs_photometric_scratch_bytes",
-                 "b200gs_depth_pearson_loss", "b200gs_hparams_advance", "b200gs_loss_accum_doubles", "b200gs_knn3"]
+                 "b200gs_depth_pearson_loss", "b200gs_hparams_advance", "b200gs_loss_accum_doubles", "b200gs_knn3", "b200gs_depth_pearson_loss_pseudo"]
 COLLECTIVE_EXPORTS = ["b200gs_allreduce_sum_f32", "b200gs_allreduce_flag_words", "b200gs_gather_reduce_f32"]
 
 EXPORTS = [
     "b200gs_version", "b200gs_last_error", "b200gs_geom_bytes", "b200gs_image_bytes", "b200gs_binning_bytes",
-    "b200gs_scratch_bytes", "b200gs_forward_preprocess", "b200gs_forward_render", "b200gs_forward",
+    "b200gs_scratch_bytes", "b200gs_workspace_init", "b200gs_forward_preprocess", "b200gs_forward_render", "b200gs_forward",
     "b200gs_forward_status", "b200gs_backward", "b200gs_mark_visible", "b200gs_geom_layout",
     "b200gs_image_layout", "b200gs_binning_layout", "b200gs_debug_sorted_keys", "b200gs_launch_count",
     "b200gs_abi_sizes", "b200gs_profile_enable", "b200gs_profile_read",
@@ -108,6 +109,7 @@ def _load():
     lib.b200gs_scratch_bytes.argtypes = [C.c_int32]
     lib.b200gs_launch_count.restype = C.c_int64
     P = C.POINTER
+    lib.b200gs_workspace_init.argtypes = [P(Workspace), C.c_int32, C.c_void_p, C.c_void_p]
     lib.b200gs_forward_preprocess.argtypes = [P(View), P(Gaussians), P(Outputs), P(Workspace), C.c_void_p, P(C.c_int64)]
     lib.b200gs_forward_render.argtypes = [P(View), P(Gaussians), P(Outputs), P(Workspace), C.c_int64, C.c_void_p]
     lib.b200gs_forward.argtypes = [P(View), P(Gaussians), P(Outputs), P(Workspace), C.c_int64, C.c_void_p]
@@ -129,6 +131,8 @@ def _load():
     lib.b200gs_depth_pearson_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                               C.c_void_p]
     lib.b200gs_loss_accum_doubles.restype = C.c_size_t
+    lib.b200gs_depth_pearson_loss_pseudo.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                                     C.c_void_p, C.c_void_p, C.c_void_p]
     lib.b200gs_knn3.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.b200gs_hparams_advance.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
     lib.b200gs_allreduce_flag_words.argtypes = [C.c_int32]

@@ -395,6 +395,9 @@ class RasterSession:
         ws.binning, ws.binning_bytes = self.binning.data_ptr(), self.binning.numel()
         self.graph = None
         self.with_backward = with_backward
+        if not with_backward:
+            ws.persistent = 1
+            check(lib.b200gs_workspace_init(C.byref(ws), P, None, _stream(dev)))
         if with_backward:
             go = grads_out or {}
             has = lambda t: t is not None
@@ -415,6 +418,9 @@ class RasterSession:
             gr.dL_dmeans3D, gr.dL_dmeans2D, gr.dL_dshs, gr.dL_dcolors = _ptr(G["means3D"]), _ptr(G["means2D"]), _ptr(G["shs"]), _ptr(G["colors_precomp"])
             gr.dL_dopacities, gr.dL_dscales, gr.dL_drotations, gr.dL_dcov3D = _ptr(G["opacities"]), _ptr(G["scales"]), _ptr(G["rotations"]), _ptr(G["cov3D"])
             gr.dL_dfeatures, gr.dL_dshs_language, gr.scratch = _ptr(G["features"]), _ptr(G["shs_language"]), self.scratch.data_ptr()
+            # persistent workspaces (b200gs_workspace_t.persistent): initialised once, left clean by the kernels, no memset per step
+            ws.persistent = 1
+            check(lib.b200gs_workspace_init(C.byref(ws), P, self.scratch.data_ptr(), _stream(dev)))
             if grad_scatter is not None:  # image-parallel training: parameter gradients are pushed to the owning ranks (parallel.FusedGradBuffer)
                 gr.scatter_bases, gr.scatter_shard_rows, gr.scatter_rank, gr.scatter_world = grad_scatter
             self.cot = dict(color=torch.zeros((3, H, W), **f32))

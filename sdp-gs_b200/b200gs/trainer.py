@@ -102,6 +102,87 @@ class GaussianTrainer:
                                  grad_scatter=self.bucket.scatter_descriptor())
             self.sessions.append(s)
         self.graphs = None
+        self.pair_graphs = {}
+        self.pseudo_sessions = []
+        if getattr(self, "pseudo_cameras", None):
+            self._build_pseudo_sessions()
+
+    # ------------------------------------------------------------------ pseudo views (train.py:138-153)
+    def add_pseudo_views(self, cameras, depth_refs):
+        """Unobserved poses rendered a second time per iteration and supervised by a monocular depth estimate only:
+        loss += w * (1 - pearson(rendered depth, depth_ref)) with depth_ref = -midas(render) in the reference (MiDaS is not
+        available offline: the caller supplies the estimate) and w = loss_scale * depth_pseudo_weight (set_pseudo_weight)."""
+        f32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(self.dev).reshape(-1).contiguous()
+        self.pseudo_cameras = list(cameras)
+        self.pseudo_ref = [f32(d) for d in depth_refs]
+        self.pseudo_w = torch.zeros((1,), dtype=torch.float32, device=self.dev)
+        self.accum_pseudo = torch.zeros((self.nacc,), dtype=torch.float64, device=self.dev)
+        self._build_pseudo_sessions()
+
+    def _build_pseudo_sessions(self):
+        P = self.P
+        self.g_means2D_pseudo = torch.zeros((P, 3), dtype=torch.float32, device=self.dev)  # not a densification input (train.py:220-221)
+        grads_out = dict(means3D=self.bucket.segment("xyz"), shs=self.bucket.segment("shs"), opacities=self.bucket.segment("opacity"),
+                         scales=self.bucket.segment("scaling"), rotations=self.bucket.segment("rotation"),
+                         shs_language=self.bucket.segment("language_feature"), means2D=self.g_means2D_pseudo)
+        self.pseudo_sessions = [rz.RasterSession(self.settings_fn(cam), means3D=self.raw["xyz"], opacities=self.act["opacity"],
+                                                 shs=self.raw["shs"].view(P, 16, 3), scales=self.act["scaling"], rotations=self.act["rotation"],
+                                                 shs_language=self.raw["feature"], extended=True, capacity=self.capacity, grads_out=grads_out,
+                                                 grad_scatter=self.bucket.scatter_descriptor())
+                                for cam in self.pseudo_cameras]
+        self.pair_graphs = {}
+
+    def set_pseudo_weight(self, w):
+        self.pseudo_w.fill_(float(w))
+
+    def _front_pseudo(self, pv, push=True):
+        """second render of the iteration: depth loss only, gradients added to the training view's."""
+        s = self.pseudo_sessions[pv]
+        s.gr.accumulate = 1
+        if self._scatter is not None:
+            s.gr.scatter_bases = self._scatter[0] if push else None
+        s.forward()
+        check(lib.b200gs_depth_pearson_loss_pseudo(s.depth.data_ptr(), self.pseudo_ref[pv].data_ptr(), self.W * self.H, self.hp_dev.data_ptr(),
+                                                   self.pseudo_w.data_ptr(), 1, self.accum_pseudo.data_ptr(), self.loss.data_ptr(),
+                                                   s.cot["depth"].data_ptr(), rz._stream()))
+        s.backward()
+
+    def step_pair(self, view, pv, adam=True, use_graph=True):
+        """One iteration with a pseudo view: train-view render + losses + backward, pseudo-view render + depth loss + backward
+        (accumulating), one Adam step.  use_graph: one CUDA graph per (view, pseudo view) pair, captured on first use (worth it
+        once densification has stopped; while the Gaussian count changes every 100 iterations the pairs recur too rarely).
+        adam=False: a densify iteration of the reference (statistics only)."""
+        self.iteration += 1
+        assert parallel.world()[1] == 1, "pseudo views are single-GPU here (as in the reference)"
+        if not adam:
+            self._front(view); self._front_pseudo(pv); self._stats_only(view)
+            return
+        if not use_graph:
+            self._front(view); self._front_pseudo(pv); self._back(view)
+            return
+        g = self.pair_graphs.get((view, pv))
+        if g is None:
+            side = torch.cuda.Stream(device=self.dev)
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(side):
+                self._front(view); self._front_pseudo(pv)
+            torch.cuda.current_stream(self.dev).wait_stream(side)
+            torch.cuda.synchronize(self.dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._front(view); self._front_pseudo(pv); self._back(view)
+            self.pair_graphs[(view, pv)] = g
+        g.replay()
+
+    def _stats_only(self, view):
+        ps = self._param_state(view)
+        check(lib.b200gs_param_step(C.byref(ps), self.hp_dev.data_ptr(), 2, rz._stream()))
+
+    def step_stats_only(self, view):
+        """A densify iteration of the reference without pseudo view: render, losses, backward, statistics; no Adam update."""
+        self.iteration += 1
+        self._front(view)
+        self._stats_only(view)
 
     # ------------------------------------------------------------------ pieces
     def _default_settings(self, cam):
@@ -323,10 +404,12 @@ class GaussianTrainer:
         proximity() (scene/gaussian_model.py:513-533, run while iteration < 2000): isolated, large Gaussians grow three
         new ones half-way to their nearest neighbours; the kNN the reference takes from its un-vendored simple_knn fork is
         b200gs_knn3 here.  Buffers are re-allocated and, with `recapture`, the per-view graphs are captured again."""
+        import time
         iteration = self.iteration if iteration is None else iteration
         if parallel.world()[1] > 1:
             self.bucket.all_reduce_statistics()
         torch.cuda.synchronize(self.dev)
+        t_start = time.perf_counter()
         self.check_overflow()
         P_before = self.P
         raw = {k: t.clone() for k, t in self.raw.items()}
@@ -389,10 +472,15 @@ class GaussianTrainer:
         # the instance count grows with the Gaussian count: keep 1.3x the largest count seen, scaled by the growth
         need = int(1.3 * self._max_rendered * max(1.0, raw["xyz"].shape[0] / max(P_before, 1))) + 4096
         self.capacity = max(self.capacity, need)
+        torch.cuda.synchronize(self.dev); t_logic = time.perf_counter()
         self._allocate(raw, m, v)
         self._refresh_activations()
+        torch.cuda.synchronize(self.dev); t_alloc = time.perf_counter()
         if recapture:
             self.capture()
+        torch.cuda.synchronize(self.dev); t_end = time.perf_counter()
+        tm = self.densify_timing = getattr(self, "densify_timing", dict(events=0, logic_s=0.0, allocate_s=0.0, capture_s=0.0))
+        tm["events"] += 1; tm["logic_s"] += t_logic - t_start; tm["allocate_s"] += t_alloc - t_logic; tm["capture_s"] += t_end - t_alloc
         return self.P
 
     def reset_opacity(self):

@@ -239,6 +239,15 @@ void b200gs_binning_layout(int32_t width, int32_t height, int64_t capacity, int6
 	off[1] = (int64_t)reinterpret_cast<size_t>(b.sorted_keys);
 }
 
+int b200gs_workspace_init(const b200gs_workspace_t* ws, int32_t P, void* scratch, void* stream_) {
+	if (!ws || !ws->geom || P < 0 || ws->geom_bytes < b200gs_geom_bytes(P)) return fail(B200GS_E_ARG, "workspace_init: bad arguments");
+	cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+	cudaError_t e = cudaMemsetAsync(ws->geom, 0, geom_zero_len(P), stream);
+	if (e == cudaSuccess && scratch) e = cudaMemsetAsync(scratch, 0, b200gs_scratch_bytes(P), stream);
+	if (e != cudaSuccess) return fail(B200GS_E_CUDA, "[CUDA ERROR] workspace_init: %s", cudaGetErrorString(e));
+	return 0;
+}
+
 int b200gs_forward_preprocess(const b200gs_view_t* v, const b200gs_gaussians_t* g, const b200gs_outputs_t* out,
                               const b200gs_workspace_t* ws, void* stream_, int64_t* num_rendered_host) {
 	if (int e = validate(v, g, ws)) return e;
@@ -249,7 +258,7 @@ int b200gs_forward_preprocess(const b200gs_view_t* v, const b200gs_gaussians_t* 
 	GeomState gs = geom_from_chunk(gbase, P);
 	ImageState is = image_from_chunk(reinterpret_cast<char*>(ws->image), v->width, v->height);
 	const size_t tiles = (size_t)((v->width + TILE_X - 1) / TILE_X) * ((v->height + TILE_Y - 1) / TILE_Y);
-	{
+	if (!ws->persistent || P == 0) {  // persistent workspaces are left clean by the previous forward's blend kernel
 		StageScope t(stream, ST_MEMSET);
 		cudaMemsetAsync(gbase, 0, geom_zero_len(P), stream);
 		if (P == 0) cudaMemsetAsync(is.ranges, 0, tiles * sizeof(uint2), stream);  // otherwise zeroed by the preprocess kernel (rasterizer_impl.cu:310)
@@ -262,7 +271,7 @@ int b200gs_forward_preprocess(const b200gs_view_t* v, const b200gs_gaussians_t* 
 	}
 	if (num_rendered_host) {
 		unsigned long long n = 0;
-		cudaError_t e = cudaMemcpyAsync(&n, &gs.hdr->num_rendered, sizeof(n), cudaMemcpyDeviceToHost, stream);
+		cudaError_t e = cudaMemcpyAsync(&n, &gs.hdr->num_acc, sizeof(n), cudaMemcpyDeviceToHost, stream);
 		if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
 		if (e != cudaSuccess) return fail(B200GS_E_CUDA, "[CUDA ERROR] reading num_rendered: %s", cudaGetErrorString(e));
 		*num_rendered_host = (int64_t)n;
@@ -292,11 +301,17 @@ static int forward_render_impl(const b200gs_view_t* v, const b200gs_gaussians_t*
 		if (int e = check_stage(v, stream, "tile sort")) return e;
 	}
 	const bool emitted = P > 0 && capacity > 0;
+	if (P > 0 && !emitted) launch_finalize_header(gs, capacity, stream);  // the status words scan_emit assigns
 	if (!emitted || !tile_counts_path((int)tiles)) {  // small tile grids: scan_emit's last CTA already built ranges + schedule
 		{ StageScope t(stream, ST_RANGES); launch_tile_ranges(*v, gs, bs, is, emitted ? capacity : 0, stream); }
 		if (int e = check_stage(v, stream, "tile ranges / schedule")) return e;
 	}
-	{ StageScope t(stream, ST_BLEND_FWD); launch_blend_forward(*v, gs, bs, is, *out, stream); }
+	{
+		StageScope t(stream, ST_BLEND_FWD);
+		char* gbase = reinterpret_cast<char*>(ws->geom);
+		launch_blend_forward(*v, gs, bs, is, *out, stream, reinterpret_cast<uint4*>(gbase + sizeof(GeomHeader)),
+		                     (geom_zero_len(P) - sizeof(GeomHeader)) / sizeof(uint4));
+	}
 	return check_stage(v, stream, "blend forward");
 }
 
@@ -347,10 +362,10 @@ int b200gs_backward(const b200gs_view_t* v, const b200gs_gaussians_t* g, const i
 	BinningState bs = binning_from_chunk(reinterpret_cast<char*>(ws->binning), v->width, v->height, capacity);
 	resolve_sorted(v, bs);
 	float* grec = reinterpret_cast<float*>(grads->scratch);
-	{ StageScope t(stream, ST_MEMSET); cudaMemsetAsync(grec, 0, b200gs_scratch_bytes(P), stream); }
+	if (!ws->persistent) { StageScope t(stream, ST_MEMSET); cudaMemsetAsync(grec, 0, b200gs_scratch_bytes(P), stream); }
 	{ StageScope t(stream, ST_BLEND_BWD); launch_blend_backward(*v, gs, bs, is, *gout, grec, stream); }
 	if (int e = check_stage(v, stream, "blend backward")) return e;
-	{ StageScope t(stream, ST_PREPROCESS_BWD); launch_preprocess_backward(*v, *g, radii, gs, grec, *grads, stream); }
+	{ StageScope t(stream, ST_PREPROCESS_BWD); launch_preprocess_backward(*v, *g, radii, gs, grec, *grads, ws->persistent != 0, stream); }
 	return check_stage(v, stream, "preprocess backward");
 }
 

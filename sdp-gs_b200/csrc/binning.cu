@@ -294,8 +294,11 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(
 		const uint32_t excl = lookback_exclusive_warp(scan_state, tile, total);
 		if (lane == 0) s_prefix = excl;
 		if (lane == 0 && (int64_t)(tile + 1) * TILE >= P) {  // last tile: instance count, overflow flag
-			const unsigned long long L = (unsigned long long)excl + total;  // == hdr->num_rendered (summed by preprocess)
-			if (L > (unsigned long long)capacity) atomicOr(&hdr->overflow, 1u);
+			// the scan's grand total IS the instance count (what the reference reads back, rasterizer_impl.cu:281): assigned here,
+			// together with the status word, so neither ever needs zeroing (preprocess accumulates its own copy in num_acc)
+			const unsigned long long L = (unsigned long long)excl + total;
+			hdr->num_rendered = L;
+			hdr->overflow = (L > (unsigned long long)capacity ? 1u : 0u) | __ldcg(&hdr->prefilter_violation);
 		}
 	}
 	__syncthreads();
@@ -485,7 +488,21 @@ __global__ void __launch_bounds__(256) debug_keys_kernel(const uint32_t* __restr
 
 }  // namespace
 
+// No instance was emitted (capacity 0): the status words scan_emit would have assigned
+__global__ void finalize_header_kernel(GeomHeader* hdr, long long capacity) {
+	pdl_trigger();
+	pdl_wait();
+	const unsigned long long L = __ldcg(&hdr->num_acc);
+	hdr->num_rendered = L;
+	hdr->overflow = (L > (unsigned long long)capacity ? 1u : 0u) | __ldcg(&hdr->prefilter_violation);
+}
+
 bool tile_counts_path(int tiles) { return tiles <= COUNT_TILES_MAX; }
+
+void launch_finalize_header(GeomState& gs, int64_t capacity, cudaStream_t stream) {
+	launch_k(PDL_EMIT, finalize_header_kernel, dim3(1), dim3(1), stream, gs.hdr, (long long)capacity);
+	count_launch();
+}
 int tile_count_stride() { return COUNT_STRIDE; }
 
 int launch_radix_sort(uint32_t* key_a, uint32_t* key_b, uint32_t* val_a, uint32_t* val_b, int64_t n_max,

@@ -161,7 +161,7 @@ struct Ticket {
 template <bool EXT>
 __global__ void __launch_bounds__(BLEND_WARPS * 32) blend_forward_kernel(
 	const uint2* ranges, const uint32_t* order, const uint32_t* point_list, const float4* rec,
-	int W, int H, int grid_x, uint32_t units, unsigned int* ticket, unsigned int* exits,
+	int W, int H, int grid_x, uint32_t units, GeomHeader* hdr, uint4* clean_words, size_t clean_count,
 	const float* __restrict__ bg, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
 	float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_alpha, float* __restrict__ out_feat)
 {
@@ -172,7 +172,16 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32) blend_forward_kernel(
 	pdl_trigger();
 	pdl_wait();
 	const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
-	const Ticket tk{ticket, exits};
+	const Ticket tk{&hdr->blend_ticket[0], &hdr->blend_exit[0]};
+	// Every kernel that used the geom workspace's counters, histograms and look-back words has completed (pdl_wait): leave
+	// them zeroed for the next forward on this workspace, so that a persistent workspace never needs a memset
+	// (b200gs_workspace_t.persistent).  num_rendered / overflow stay: they are assigned, not accumulated.
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < clean_count; i += (size_t)gridDim.x * blockDim.x)
+		clean_words[i] = make_uint4(0u, 0u, 0u, 0u);
+	if (blockIdx.x == 0 && threadIdx.x < 8) hdr->sort_ticket[threadIdx.x] = 0u;
+	if (blockIdx.x == 0 && threadIdx.x == 8) {
+		hdr->scan_ticket = 0u; hdr->ranges_done = 0u; hdr->emit_done = 0u; hdr->num_acc = 0ull; hdr->prefilter_violation = 0u;
+	}
 
 	for (uint32_t unit = tk.next(lane); unit < units; unit = tk.next(lane)) {
 		const Unit u = make_unit(unit, order, ranges, W, H, grid_x);
@@ -548,11 +557,9 @@ cudaError_t launch_blend(unsigned site, void (*kernel)(KArgs...), unsigned grid,
 }  // namespace
 
 void launch_blend_forward(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
-                          const b200gs_outputs_t& out, cudaStream_t stream) {
+                          const b200gs_outputs_t& out, cudaStream_t stream, uint4* clean_words, size_t clean_count) {
 	const int gx = (v.width + TILE_X - 1) / TILE_X, gy = (v.height + TILE_Y - 1) / TILE_Y;
 	const unsigned units = (unsigned)(gx * gy * 8);
-	unsigned int* ticket = &gs.hdr->blend_ticket[0];
-	unsigned int* exits = &gs.hdr->blend_exit[0];
 	if (v.extended) {
 		static unsigned cap = 0;
 		constexpr size_t smem = BLEND_WARPS * sizeof(FwdSmem<true>);
@@ -560,7 +567,7 @@ void launch_blend_forward(const b200gs_view_t& v, GeomState& gs, BinningState& b
 		const unsigned want = (units + BLEND_WARPS - 1) / BLEND_WARPS;
 		launch_blend(PDL_BLEND_FWD, blend_forward_kernel<true>, want < cap ? want : cap, smem, stream, (const uint2*)is.ranges,
 			(const uint32_t*)is.tile_order, (const uint32_t*)bs.sorted_vals, (const float4*)gs.rec,
-			v.width, v.height, gx, units, ticket, exits, v.background, is.final_T, is.n_contrib, out.color, out.depth, out.alpha, out.feature);
+			v.width, v.height, gx, units, gs.hdr, clean_words, clean_count, v.background, is.final_T, is.n_contrib, out.color, out.depth, out.alpha, out.feature);
 	} else {
 		static unsigned cap = 0;
 		constexpr size_t smem = BLEND_WARPS * sizeof(FwdSmem<false>);
@@ -568,7 +575,7 @@ void launch_blend_forward(const b200gs_view_t& v, GeomState& gs, BinningState& b
 		const unsigned want = (units + BLEND_WARPS - 1) / BLEND_WARPS;
 		launch_blend(PDL_BLEND_FWD, blend_forward_kernel<false>, want < cap ? want : cap, smem, stream, (const uint2*)is.ranges,
 			(const uint32_t*)is.tile_order, (const uint32_t*)bs.sorted_vals, (const float4*)gs.rec,
-			v.width, v.height, gx, units, ticket, exits, v.background, is.final_T, is.n_contrib, out.color, (float*)nullptr, (float*)nullptr, (float*)nullptr);
+			v.width, v.height, gx, units, gs.hdr, clean_words, clean_count, v.background, is.final_T, is.n_contrib, out.color, (float*)nullptr, (float*)nullptr, (float*)nullptr);
 	}
 	count_launch();
 }

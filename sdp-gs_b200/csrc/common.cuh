@@ -21,15 +21,17 @@
 #define GREC_FLOATS 16
 
 struct GeomHeader {  // first 256 bytes of the geom workspace
-	unsigned long long num_rendered;  // inclusive-scan total of tiles touched
-	unsigned int overflow;            // set when num_rendered > binning capacity
+	unsigned long long num_rendered;  // inclusive-scan total of tiles touched: ASSIGNED by scan_emit's last tile (never needs zeroing)
+	unsigned int overflow;            // bit 0: num_rendered > binning capacity, bit 1: prefilter violation; assigned with num_rendered
 	unsigned int scan_ticket;         // dynamic tile id allocator for the look-back scan
 	unsigned int sort_ticket[8];      // one per radix pass (4 depth passes + up to 4 tile passes)
 	unsigned int ranges_done;         // CTAs of the tile-ranges kernel that have finished (last one builds the blend schedule)
 	unsigned int emit_done;           // CTAs of scan_emit that have finished (last one turns tile counts into ranges + schedule)
 	unsigned int blend_ticket[2];     // next blend unit to hand out (forward, backward): persistent warps draw from it
 	unsigned int blend_exit[2];       // warps that have run dry; the last one re-arms ticket and counter
-	unsigned int pad[46];
+	unsigned long long num_acc;       // instance count accumulated by the preprocess kernel (num_rendered is assigned from the scan)
+	unsigned int prefilter_violation; // 2 when a Gaussian was culled although `prefiltered` was set
+	unsigned int pad[43];
 };
 static_assert(sizeof(GeomHeader) == 256, "header size");
 
@@ -93,7 +95,7 @@ void count_launch(int n = 1);
 void launch_preprocess_forward(const b200gs_view_t& v, const b200gs_gaussians_t& g, int32_t* radii, GeomState& gs,
                                ImageState& is, cudaStream_t stream);
 void launch_preprocess_backward(const b200gs_view_t& v, const b200gs_gaussians_t& g, const int32_t* radii,
-                                GeomState& gs, const float* grec, const b200gs_grads_t& gr, cudaStream_t stream);
+                                GeomState& gs, float* grec, const b200gs_grads_t& gr, bool rezero_grec, cudaStream_t stream);
 void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t stream);
 
 // stable LSD radix sort of (u32 key, u32 value) pairs on key bits [0, end_bit); n is read from
@@ -113,7 +115,8 @@ void launch_debug_keys(const b200gs_view_t& v, GeomState& gs, BinningState& bs, 
                        cudaStream_t stream);
 
 void launch_blend_forward(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
-                          const b200gs_outputs_t& out, cudaStream_t stream);
+                          const b200gs_outputs_t& out, cudaStream_t stream, uint4* clean_words, size_t clean_count);
+void launch_finalize_header(GeomState& gs, int64_t capacity, cudaStream_t stream);
 void launch_blend_backward(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
                            const b200gs_grad_outputs_t& gout, float* grec, cudaStream_t stream);
 

@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(
 	const float x = s_means[3 * li], y = s_means[3 * li + 1], z = s_means[3 * li + 2];
 	const float pz = xform_row(v, 2, x, y, z);
 	bool alive = !(pz <= 0.2f);  // in_frustum, auxiliary.h:154
-	if (!alive && prefiltered) atomicOr(&hdr->overflow, 2u);  // reference: printf + __trap (auxiliary.h:156-160)
+	if (!alive && prefiltered) atomicOr(&hdr->prefilter_violation, 2u);  // reference: printf + __trap (auxiliary.h:156-160)
 
 	if (alive) {
 		const float hx = xform_row(vc.proj, 0, x, y, z), hy = xform_row(vc.proj, 1, x, y, z);
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(
 		tma_store_wait_read();
 	}
 	// num_rendered = total number of (Gaussian, tile) instances (what the reference reads back after its scan, rasterizer_impl.cu:281)
-	if (threadIdx.x == 0 && s_instances) atomicAdd(&hdr->num_rendered, s_instances);
+	if (threadIdx.x == 0 && s_instances) atomicAdd(&hdr->num_acc, s_instances);
 	for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) {
 		const uint32_t c = (&s_hist[0][0])[i];
 		if (c) atomicAdd(depth_hist + i, c);
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_backward_kernel(
 	const float* __restrict__ feat_precomp, const float* __restrict__ shs_language, const float* __restrict__ confidence,
 	const float* __restrict__ viewmatrix, const float* __restrict__ projmatrix, const float* __restrict__ campos,
 	float focal_x, float focal_y, float tan_fovx, float tan_fovy, int extended,
-	const float4* __restrict__ grec,
+	float4* grec, int rezero_grec,
 	float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dshs,
 	float* __restrict__ dL_dcolors, float* __restrict__ dL_dopac, float* __restrict__ dL_dscales,
 	float* __restrict__ dL_drots, float* __restrict__ dL_dcov3D, float* __restrict__ dL_dfeat,
@@ -738,6 +738,11 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_backward_kernel(
 		for (int i = li; i < n / 4; i += PRE_THREADS) reinterpret_cast<float4*>(g)[i] = reinterpret_cast<const float4*>(src)[i];
 		for (int i = (n & ~3) + li; i < n; i += PRE_THREADS) g[i] = src[i];
 	};
+	if (rezero_grec && valid) {  // persistent workspaces: the scratch rows this thread consumed are zero again for the next backward
+		const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+		float4* row = grec + 4 * (size_t)idx;
+		row[0] = z; row[1] = z; row[2] = z; row[3] = z;
+	}
 	if (accumulate) {
 		auto add_local = [&](const float* local, float* stage, int floats_per_item) {
 			if (local == nullptr) return;
@@ -791,7 +796,7 @@ void launch_preprocess_forward(const b200gs_view_t& v, const b200gs_gaussians_t&
 }
 
 void launch_preprocess_backward(const b200gs_view_t& v, const b200gs_gaussians_t& g, const int32_t* radii,
-                                GeomState& gs, const float* grec, const b200gs_grads_t& gr, cudaStream_t stream) {
+                                GeomState& gs, float* grec, const b200gs_grads_t& gr, bool rezero_grec, cudaStream_t stream) {
 	const int P = g.P;
 	const float focal_y = v.height / (2.0f * v.tan_fovy);
 	const float focal_x = v.width / (2.0f * v.tan_fovx);
@@ -803,7 +808,7 @@ void launch_preprocess_backward(const b200gs_view_t& v, const b200gs_gaussians_t
 	launch_k(PDL_PRE_BWD, preprocess_backward_kernel, dim3((P + PRE_THREADS - 1) / PRE_THREADS), dim3(PRE_THREADS), stream,
 		P, v.sh_degree, v.sh_coeffs, g.means3D, radii, g.shs, gs.clamped, g.scales, g.rotations, v.scale_modifier,
 		g.cov3D_precomp, g.language_feature_precomp, g.shs_language, g.confidence, v.viewmatrix, v.projmatrix,
-		v.campos, focal_x, focal_y, v.tan_fovx, v.tan_fovy, v.extended, reinterpret_cast<const float4*>(grec),
+		v.campos, focal_x, focal_y, v.tan_fovx, v.tan_fovy, v.extended, reinterpret_cast<float4*>(grec), rezero_grec ? 1 : 0,
 		gr.dL_dmeans3D, gr.dL_dmeans2D, gr.dL_dshs, gr.dL_dcolors, gr.dL_dopacities, gr.dL_dscales,
 		gr.dL_drotations, gr.dL_dcov3D, gr.dL_dfeatures, gr.dL_dshs_language, tma_ok, gr.scatter_bases,
 		(long long)gr.scatter_shard_rows, (int)gr.scatter_rank, (int)gr.accumulate);

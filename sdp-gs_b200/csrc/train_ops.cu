@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(LT * LT) ssim_l1_backward_kernel(
 __global__ void __launch_bounds__(256) pearson_reduce_kernel(
 	const float* __restrict__ depth, const float* __restrict__ mono, int n,
 	double* __restrict__ accum /*[ACC_SLOTS][16] partial sums (8 used), then counter, then 4 coefficients*/,
-	const b200gs_hparams_t* __restrict__ hp, double* __restrict__ loss_out)
+	const b200gs_hparams_t* __restrict__ hp, double* __restrict__ loss_out, const float* __restrict__ weight_override, int single_branch)
 {
 	__shared__ double red[8][8];
 	pdl_trigger();
@@ -254,8 +254,10 @@ __global__ void __launch_bounds__(256) pearson_reduce_kernel(
 			const double D1 = sqrt(S11 * Syy), D2 = sqrt(S22 * Syy);
 			double r1 = S1y / D1, r2 = S2y / D2;
 			r1 = fmin(1.0, fmax(-1.0, r1)); r2 = fmin(1.0, fmax(-1.0, r2));
-			const double w = (double)hp->depth_weight;
-			const bool first = (1.0 - r1) <= (1.0 - r2);  // python min(a, b) returns a on ties
+			// pseudo views (train.py:143-153): weight = loss_scale * depth_pseudo_weight from its own device word, and the single
+			// correlation 1 - pearson(depth, -midas) instead of the min over the two forms
+			const double w = weight_override ? (double)__ldcg(weight_override) : (double)hp->depth_weight;
+			const bool first = single_branch || (1.0 - r1) <= (1.0 - r2);  // python min(a, b) returns a on ties
 			const double r = first ? r1 : r2, D = first ? D1 : D2, mx = first ? m1 : m2;
 			double* coef = accum + 16 * ACC_SLOTS + 2;
 			coef[0] = -w / D;                               // A
@@ -299,8 +301,11 @@ __device__ __forceinline__ float adam1(float& p, float& m, float& v, float g, fl
 	return p;
 }
 
-__global__ void __launch_bounds__(256) param_step_kernel(b200gs_param_state_t s, const b200gs_hparams_t* __restrict__ hp, int update)
+__global__ void __launch_bounds__(256) param_step_kernel(b200gs_param_state_t s, const b200gs_hparams_t* __restrict__ hp, int mode)
 {
+	const bool update = mode == 1;   // Adam update + statistics; mode 2: statistics only (the reference's densify iterations, where the
+	                                 // freshly re-created parameters have no gradient and optimizer.step() changes nothing)
+
 	pdl_trigger();
 	pdl_wait();
 	const b200gs_hparams_t h = *hp;
@@ -369,7 +374,7 @@ __global__ void __launch_bounds__(256) param_step_kernel(b200gs_param_state_t s,
 		reinterpret_cast<float4*>(s.rotation_act)[i] = make_float4(q.x * inv2, q.y * inv2, q.z * inv2, q.w * inv2);
 	}
 	// densification statistics of this step's view (train.py:218-221, scene/gaussian_model.py:610-612)
-	if (update && s.xyz_gradient_accum) {
+	if (mode != 0 && s.xyz_gradient_accum) {
 		for (size_t i = tid; i < P; i += nth) {
 			const int r = __ldcg(s.radii + i);
 			if (r > 0) {
@@ -472,12 +477,18 @@ int b200gs_photometric_loss(const float* image, const float* gt, int32_t width, 
 
 int b200gs_depth_pearson_loss(const float* depth, const float* depth_mono, int32_t n, const b200gs_hparams_t* hp,
                               double* accum, double* loss_out, float* dL_ddepth, void* stream_) {
-	if (!depth || !depth_mono || !hp || !accum || !loss_out || !dL_ddepth || n <= 0)
+	return b200gs_depth_pearson_loss_pseudo(depth, depth_mono, n, hp, nullptr, 0, accum, loss_out, dL_ddepth, stream_);
+}
+
+int b200gs_depth_pearson_loss_pseudo(const float* depth, const float* depth_ref, int32_t n, const b200gs_hparams_t* hp,
+                                     const float* weight_device, int32_t single_branch, double* accum, double* loss_out,
+                                     float* dL_ddepth, void* stream_) {
+	if (!depth || !depth_ref || !hp || !accum || !loss_out || !dL_ddepth || n <= 0)
 		return train_fail(B200GS_E_ARG, "depth_pearson_loss: bad arguments");
 	cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
 	const unsigned grid = (unsigned)min((n + 255) / 256, 148 * 4);
-	launch_k(PDL_TRAIN, pearson_reduce_kernel, dim3(grid), dim3(256), stream, depth, depth_mono, (int)n, accum, hp, loss_out);
-	launch_k(PDL_TRAIN, pearson_grad_kernel, dim3(grid), dim3(256), stream, depth, depth_mono, (int)n, (const double*)(accum + 16 * ACC_SLOTS + 2), dL_ddepth);
+	launch_k(PDL_TRAIN, pearson_reduce_kernel, dim3(grid), dim3(256), stream, depth, depth_ref, (int)n, accum, hp, loss_out, weight_device, (int)single_branch);
+	launch_k(PDL_TRAIN, pearson_grad_kernel, dim3(grid), dim3(256), stream, depth, depth_ref, (int)n, (const double*)(accum + 16 * ACC_SLOTS + 2), dL_ddepth);
 	count_launch(2);
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return train_fail(B200GS_E_CUDA, cudaGetErrorString(e));
@@ -510,7 +521,7 @@ int b200gs_param_step(const b200gs_param_state_t* s, const b200gs_hparams_t* hp,
 	if (s->P == 0) return 0;
 	if (!s->xyz || !s->shs || !s->opacity || !s->scaling || !s->rotation || !s->opacity_act || !s->scaling_act || !s->rotation_act)
 		return train_fail(B200GS_E_ARG, "param_step: parameter pointers are required");
-	if (update && (!s->g_xyz || !s->g_shs || !s->g_opacity || !s->g_scaling || !s->g_rotation || !s->m_xyz || !s->v_xyz ||
+	if (update == 1 && (!s->g_xyz || !s->g_shs || !s->g_opacity || !s->g_scaling || !s->g_rotation || !s->m_xyz || !s->v_xyz ||
 	               !s->m_shs || !s->v_shs || !s->m_opacity || !s->v_opacity || !s->m_scaling || !s->v_scaling || !s->m_rotation ||
 	               !s->v_rotation || (s->feature && (!s->g_feature || !s->m_feature || !s->v_feature))))
 		return train_fail(B200GS_E_ARG, "param_step: gradients and Adam moments are required for an update");
