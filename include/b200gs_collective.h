@@ -9,7 +9,9 @@
  * every rank's peer-mapped allocation, e.g. torch.distributed._symmetric_memory).  Two-shot algorithm: rank r sums
  * slice r of all ranks' buffers in rank order 0..world-1 (bit-identical result everywhere) and writes it back to
  * every rank.  `flags` is a zero-initialised symmetric u32 array of b200gs_allreduce_flag_words(world) words used for
- * the two block-level barriers (self-resetting, so the call can be captured in a CUDA graph and replayed). */
+ * the two block-level barriers: one-way epoch flags (a rank stores the launch's epoch into its slot on every peer and
+ * spins on its own memory; the epoch counter lives in the same array, so the call can be captured in a CUDA graph and
+ * replayed).  All ranks must issue the same sequence of collective calls on a given flag array. */
 #ifndef B200GS_COLLECTIVE_H_
 #define B200GS_COLLECTIVE_H_
 

@@ -17,23 +17,35 @@ constexpr int AR_BLOCKS = 256;   // maximum grid (sizes the flag array); the lau
 constexpr int AR_THREADS = 512;
 constexpr int AR_MAX_WORLD = 8;
 
-__device__ __forceinline__ void flag_put(uint32_t* addr) {
-	while (atomicCAS_system(addr, 0u, 1u) != 0u) {}
+// One-way epoch flags: a rank announces itself by STORING the launch's epoch into its slot of every peer's flag array
+// (a posted NVLink write -- no round trip, unlike the compare-and-swap handshake this replaced) and waits, spinning on
+// its own memory, until every peer's slot shows the same epoch.  The epoch is a per-block launch counter kept in the
+// rank's own flag array (every rank launches the same sequence of collectives with the same grid, so the counters
+// agree); it lives in device memory, so a captured CUDA graph replays correctly.  A peer is never more than one
+// barrier ahead (it needs this rank's store to get any further), and the two barriers of a launch use separate slots.
+__device__ __forceinline__ void st_flag(uint32_t* addr, uint32_t v) {
+	asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");  // ordered by the system fence before it
 }
-__device__ __forceinline__ void flag_wait(uint32_t* addr) {
-	while (atomicCAS_system(addr, 1u, 0u) != 1u) {}
+__device__ __forceinline__ uint32_t ld_flag(const uint32_t* addr) {
+	uint32_t v;
+	asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");  // the system fence after the spin orders what follows
+	return v;
+}
+__device__ __forceinline__ uint32_t* epoch_word(void* const* flags, int rank) {
+	return reinterpret_cast<uint32_t*>(flags[rank]) + (size_t)2 * AR_BLOCKS * AR_MAX_WORLD + blockIdx.x;
 }
 
-// Block b of every rank meets block b of every other rank.  Slot layout of a rank's flag array: [phase][block][source rank].
-__device__ __forceinline__ void block_barrier(void* const* flags, int rank, int world, int phase) {
+// Block b of every rank meets block b of every other rank.  Slot layout of a rank's flag array: [phase][block][source rank],
+// then one launch counter per block.
+__device__ __forceinline__ void block_barrier(void* const* flags, int rank, int world, int phase, uint32_t epoch) {
 	__syncthreads();
 	if ((int)threadIdx.x < world) {
 		const int peer = threadIdx.x;
-		__threadfence_system();
-		uint32_t* theirs = reinterpret_cast<uint32_t*>(flags[peer]) + ((size_t)phase * gridDim.x + blockIdx.x) * AR_MAX_WORLD + rank;
-		uint32_t* mine = reinterpret_cast<uint32_t*>(flags[rank]) + ((size_t)phase * gridDim.x + blockIdx.x) * AR_MAX_WORLD + peer;
-		flag_put(theirs);
-		flag_wait(mine);
+		__threadfence_system();  // everything this block wrote (observed through the barrier above) is ordered before the flag
+		uint32_t* theirs = reinterpret_cast<uint32_t*>(flags[peer]) + ((size_t)phase * AR_BLOCKS + blockIdx.x) * AR_MAX_WORLD + rank;
+		const uint32_t* mine = reinterpret_cast<uint32_t*>(flags[rank]) + ((size_t)phase * AR_BLOCKS + blockIdx.x) * AR_MAX_WORLD + peer;
+		st_flag(theirs, epoch);
+		while (ld_flag(mine) != epoch) {}
 		__threadfence_system();
 	}
 	__syncthreads();
@@ -49,7 +61,8 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_p2p_kernel(void* const* 
 	for (int r = 0; r < WORLD; r++) p[r] = reinterpret_cast<float4*>(bufs[r]) + off4;
 	if ((int)threadIdx.x < WORLD) s_flags[threadIdx.x] = flags[threadIdx.x];
 	__syncthreads();
-	block_barrier(s_flags, rank, WORLD, 0);  // every rank's producer kernels have finished (stream order) before its flags go up
+	const uint32_t epoch = *epoch_word(s_flags, rank) + 1u;
+	block_barrier(s_flags, rank, WORLD, 0, epoch);  // every rank's producer kernels have finished (stream order) before its flags go up
 	const int64_t per = (n4 + WORLD - 1) / WORLD;
 	const int64_t lo = per * rank, hi = min(n4, lo + per);
 	constexpr int AR_UNROLL = WORLD <= 2 ? 8 : (WORLD <= 4 ? 4 : 2);
@@ -74,7 +87,8 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_p2p_kernel(void* const* 
 			}
 		}
 	}
-	block_barrier(s_flags, rank, WORLD, 1);  // every slice has landed everywhere
+	block_barrier(s_flags, rank, WORLD, 1, epoch);  // every slice has landed everywhere
+	if (threadIdx.x == 0) *epoch_word(s_flags, rank) = epoch;
 }
 
 __global__ void __launch_bounds__(AR_THREADS) allreduce_multimem_kernel(void* const* __restrict__ flags, float4* mc, int64_t off4, int64_t n4,
@@ -83,7 +97,8 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_multimem_kernel(void* co
 	__shared__ void* s_flags[AR_MAX_WORLD];
 	if ((int)threadIdx.x < world) s_flags[threadIdx.x] = flags[threadIdx.x];
 	__syncthreads();
-	block_barrier(s_flags, rank, world, 0);
+	const uint32_t epoch = *epoch_word(s_flags, rank) + 1u;
+	block_barrier(s_flags, rank, world, 0, epoch);
 	const int64_t per = (n4 + world - 1) / world;
 	const int64_t lo = per * rank, hi = min(n4, lo + per);
 	for (int64_t i = lo + (int64_t)blockIdx.x * AR_THREADS + threadIdx.x; i < hi; i += (int64_t)gridDim.x * AR_THREADS) {
@@ -93,7 +108,8 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_multimem_kernel(void* co
 		             : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(addr) : "memory");
 		asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
 	}
-	block_barrier(s_flags, rank, world, 1);
+	block_barrier(s_flags, rank, world, 1, epoch);
+	if (threadIdx.x == 0) *epoch_word(s_flags, rank) = epoch;
 }
 
 // Gather half of the fused gradient exchange (include/b200gs_collective.h: b200gs_gather_reduce_f32).
@@ -110,7 +126,8 @@ __global__ void __launch_bounds__(AR_THREADS) gather_reduce_kernel(void* const* 
 	pdl_trigger();
 	pdl_wait();  // this rank's own pushes (the backward kernel just before) are complete
 	__syncthreads();
-	block_barrier(s_flags, rank, WORLD, 0);  // ... and so are everybody else's
+	const uint32_t epoch = *epoch_word(s_flags, rank) + 1u;
+	block_barrier(s_flags, rank, WORLD, 0, epoch);  // ... and so are everybody else's
 	const int64_t Pp4 = Ps * WORLD / 4, Ps4 = Ps / 4;  // Ps % 128 == 0
 	const int64_t n4 = Ps4 * 62, src_stride4 = Ps4 * 64;
 	constexpr int UNROLL = WORLD <= 2 ? 4 : 2;
@@ -139,7 +156,8 @@ __global__ void __launch_bounds__(AR_THREADS) gather_reduce_kernel(void* const* 
 			for (int r = 0; r < WORLD; r++) __stcg(out[r] + o, a);
 		}
 	}
-	block_barrier(s_flags, rank, WORLD, 1);  // every shard has landed everywhere
+	block_barrier(s_flags, rank, WORLD, 1, epoch);  // every shard has landed everywhere
+	if (threadIdx.x == 0) *epoch_word(s_flags, rank) = epoch;
 }
 
 int ar_blocks() {
@@ -156,7 +174,7 @@ int ar_blocks() {
 
 extern "C" {
 
-size_t b200gs_allreduce_flag_words(int32_t world) { (void)world; return (size_t)2 * AR_BLOCKS * AR_MAX_WORLD; }
+size_t b200gs_allreduce_flag_words(int32_t world) { (void)world; return (size_t)2 * AR_BLOCKS * AR_MAX_WORLD + AR_BLOCKS; }
 
 int b200gs_allreduce_sum_f32(void* const* buffers_dev, void* const* flags_dev, void* multicast_ptr, int64_t offset_floats,
                              int64_t n_floats, int32_t rank, int32_t world, void* stream_) {

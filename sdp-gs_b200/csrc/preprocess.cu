@@ -6,6 +6,7 @@
 // are part of the bit-exact contract, so every operation that feeds them is written with
 // round-to-nearest intrinsics in the order the reference's sm_100a build executes them (read off
 // its SASS: cicc *and* ptxas contract mul+add into fma there, e.g. det = fma(a, c, -(b*b))).
+#include <cstdlib>
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_backward_kernel(
 	float* __restrict__ dL_dcolors, float* __restrict__ dL_dopac, float* __restrict__ dL_dscales,
 	float* __restrict__ dL_drots, float* __restrict__ dL_dcov3D, float* __restrict__ dL_dfeat,
 	float* __restrict__ dL_dshs_lang, int tma_ok, void* const* __restrict__ scatter_bases, long long scatter_Ps, int scatter_rank,
-	int accumulate)
+	int accumulate, int scatter_tma)
 {
 	// inputs staged as in the forward; the same buffers are reused for the outgoing gradients (a thread only ever
 	// touches its own row), which leave as contiguous bulk stores instead of 12/24/192-byte strided scalar stores
@@ -734,6 +735,10 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_backward_kernel(
 	};
 	auto push = [&](int seg, const float* src, int floats_per_item) {  // rows li0.. of segment `seg` in the owner's staging block
 		float* g = fb + (size_t)seg * (size_t)scatter_Ps + li0 * floats_per_item;  // 16-byte aligned: Ps and li0 are multiples of 128
+		if (full && scatter_tma) {  // one bulk copy per array through the TMA engine instead of 16-byte LSU stores
+			if (li == 0) tma_store_1d(g, src, (uint32_t)(PRE_THREADS * floats_per_item * 4));
+			return;
+		}
 		const int n = cnt * floats_per_item;
 		for (int i = li; i < n / 4; i += PRE_THREADS) reinterpret_cast<float4*>(g)[i] = reinterpret_cast<const float4*>(src)[i];
 		for (int i = (n & ~3) + li; i < n; i += PRE_THREADS) g[i] = src[i];
@@ -805,13 +810,15 @@ void launch_preprocess_backward(const b200gs_view_t& v, const b200gs_gaussians_t
 	                   al16(g.shs_language) && al16(g.confidence) && al16(grec) && al16(gr.dL_dmeans3D) && al16(gr.dL_dmeans2D) &&
 	                   al16(gr.dL_dshs) && al16(gr.dL_dcolors) && al16(gr.dL_dscales) && al16(gr.dL_dcov3D) && al16(gr.dL_dfeatures) &&
 	                   al16(gr.dL_dshs_language);
+	static int scatter_tma = -1;  // B200GS_SCATTER_TMA=0: plain stores to the peer staging blocks (A/B)
+	if (scatter_tma < 0) { const char* e = getenv("B200GS_SCATTER_TMA"); scatter_tma = e ? atoi(e) : 1; }
 	launch_k(PDL_PRE_BWD, preprocess_backward_kernel, dim3((P + PRE_THREADS - 1) / PRE_THREADS), dim3(PRE_THREADS), stream,
 		P, v.sh_degree, v.sh_coeffs, g.means3D, radii, g.shs, gs.clamped, g.scales, g.rotations, v.scale_modifier,
 		g.cov3D_precomp, g.language_feature_precomp, g.shs_language, g.confidence, v.viewmatrix, v.projmatrix,
 		v.campos, focal_x, focal_y, v.tan_fovx, v.tan_fovy, v.extended, reinterpret_cast<float4*>(grec), rezero_grec ? 1 : 0,
 		gr.dL_dmeans3D, gr.dL_dmeans2D, gr.dL_dshs, gr.dL_dcolors, gr.dL_dopacities, gr.dL_dscales,
 		gr.dL_drotations, gr.dL_dcov3D, gr.dL_dfeatures, gr.dL_dshs_language, tma_ok, gr.scatter_bases,
-		(long long)gr.scatter_shard_rows, (int)gr.scatter_rank, (int)gr.accumulate);
+		(long long)gr.scatter_shard_rows, (int)gr.scatter_rank, (int)gr.accumulate, scatter_tma);
 	count_launch();
 }
 
