@@ -519,20 +519,31 @@ def run_b200gs(args, rank, world, local):
     dom = max((k for k in by_stage if k not in ("depth_sort",)), key=lambda k: stage_ms[k] if k != "tile_sort" else sort_ms)
     dom_ms = sort_ms if dom == "tile_sort" else stage_ms[dom]
     achieved = by_stage[dom] / (dom_ms * 1e-3) / 1e9
-    traffic = None
+    # DRAM traffic and warp-instruction count of the dominant kernel from the committed ncu capture -- only when that capture
+    # was taken on the workload being run (profiles/traffic.json names it); null otherwise
+    traffic, issue = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and args.P is None:
         try:
-            traffic = json.load(open(tpath)).get(dom)
+            tj = json.load(open(tpath))
+            if tj.get("workload") == args.workload and tj.get("mode") == args.mode:
+                traffic = tj.get("dram_bytes", {}).get(dom)
+                inst = tj.get("warp_instructions", {}).get(dom)
+                if inst and clocks.get("sm_mhz"):
+                    slots = tj.get("issue_slots_per_cycle", 592)
+                    # the ceiling that does bind the blend kernels: warp instructions issued / issue slots available in the kernel's time
+                    issue = dict(warp_instructions=inst, slots_per_cycle=slots, sm_mhz=clocks["sm_mhz"],
+                                 frac=inst / (slots * clocks["sm_mhz"] * 1e6 * dom_ms * 1e-3),
+                                 floor_us=inst / (slots * clocks["sm_mhz"]), source="smsp__inst_executed.sum, profiles/r02_blend_ncu_full_summary.csv")
         except Exception:
-            traffic = None
+            traffic, issue = None, None
     total_bytes = model["bytes_fwd"] + model["bytes_bwd"]
-    roofline = dict(bound="hbm", kernel=dom, achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
+    roofline = dict(bound="hbm", kernel=dom, achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic, issue=issue,
                     peak_source=peak_src, algorithmic_bytes=by_stage[dom], kernel_ms=dom_ms,
                     step=dict(algorithmic_bytes=total_bytes, achieved=total_bytes / (ms_per_step * 1e-3) / 1e9,
                               frac=total_bytes / (ms_per_step * 1e-3) / 1e9 / peak),
                     stage_ms=stage_ms, stage_sum_ms=sum(stage_ms.values()),
-                    note="blend stages are FP32/SFU bound (256*L pair evaluations), not HBM bound; see DESIGN.md")
+                    note="the blend kernels are issue-slot bound (FP32 pair evaluation), not HBM bound: `issue.frac` is the fraction that describes them; see DESIGN.md")
 
     train = None
     if not args.fwd_only and ext and not args.no_train:
