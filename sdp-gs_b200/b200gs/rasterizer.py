@@ -344,6 +344,33 @@ def launch_count():
     return int(lib.b200gs_launch_count())
 
 
+_WARMED = set()  # (device index) whose kernels have been launched once outside a capture (lazy module loading)
+
+
+def capture_graph(fn, device, warmup=None):
+    """Capture `fn` into a CUDA graph on a side stream with the raw capture_begin / capture_end calls.  `torch.cuda.graph`
+    would also run gc.collect() and torch.cuda.empty_cache() on entry -- milliseconds each, which is most of the cost of
+    re-capturing after a densification.  Nothing inside `fn` may allocate through torch (the b200gs calls never do).
+    `warmup` (default: fn) runs once per device before the first capture: lazy module loading must not happen while capturing."""
+    key = torch.device(device).index
+    side = torch.cuda.Stream(device=device)
+    side.wait_stream(torch.cuda.current_stream(device))
+    if key not in _WARMED:
+        with torch.cuda.stream(side):
+            (warmup or fn)()
+        torch.cuda.synchronize(device)
+        _WARMED.add(key)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        g.capture_begin()
+        try:
+            fn()
+        finally:
+            g.capture_end()
+    torch.cuda.current_stream(device).wait_stream(side)
+    return g
+
+
 class RasterSession:
     """Pre-planned forward(+backward) over fixed device buffers: no allocation, no host sync, so a whole
     step can be captured once into a CUDA graph and replayed (`capture()` / `replay()`).
@@ -452,7 +479,7 @@ class RasterSession:
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(s):
-            fn()  # warm-up outside capture (lazy module loading must not happen while capturing)
+            fn()  # warm-up outside capture (lazy module loading must not happen while capturing; `fn` may launch foreign kernels)
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
         self.graph = torch.cuda.CUDAGraph()

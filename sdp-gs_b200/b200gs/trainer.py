@@ -305,26 +305,21 @@ class GaussianTrainer:
         """Capture one CUDA graph per view (front [+ back when single-GPU])."""
         world = parallel.world()[1]
         self.graphs = []
-        side = torch.cuda.Stream(device=self.dev)
         for v in range(len(self.sessions)):
-            side.wait_stream(torch.cuda.current_stream(self.dev))
-            with torch.cuda.stream(side):  # warm-up outside capture (lazy module loading must not happen while capturing)
-                self._front(v)
-            torch.cuda.current_stream(self.dev).wait_stream(side)
-            torch.cuda.synchronize(self.dev)
-            own_collective = world > 1 and self.bucket._symm is not None  # our all-reduce kernel can live inside the graph
-            ga = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(ga):
+            own_collective = world > 1 and self.bucket._symm is not None  # our exchange kernels can live inside the graph
+
+            def body(v=v, own_collective=own_collective):
                 self._front(v)
                 if own_collective:
                     self._exchange()
                 if world == 1 or own_collective:
                     self._back(v)
+
+            # the one-time warm-up runs the front part only (no parameter is changed outside a real step)
+            ga = rz.capture_graph(body, self.dev, warmup=lambda v=v: self._front(v))
             gb = None
             if world > 1 and not own_collective:
-                gb = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gb):
-                    self._back(v)
+                gb = rz.capture_graph(lambda v=v: self._back(v), self.dev, warmup=lambda: None)
             self.graphs.append((ga, gb))
         # the warm-up / capture passes ran the front part with the initial hparams only: no parameter was changed
         return self

@@ -17,6 +17,7 @@
 // histograms of ALL passes are produced by the kernel that writes the keys (preprocess for the
 // depth keys, scan_emit for the tile keys), not by a separate read of the keys or inside the passes.
 #include <cstddef>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -25,8 +26,11 @@ constexpr uint32_t FLAG_LOCAL = 1u << 30;   // word holds this tile's own count
 constexpr uint32_t FLAG_INCL = 2u << 30;    // word holds the inclusive count over tiles [0..t]
 constexpr uint32_t FLAG_MASK = 3u << 30;
 constexpr uint32_t VALUE_MASK = ~FLAG_MASK;
-constexpr int LOOKBACK_WINDOW = 8;          // predecessors inspected per step (independent loads in flight): the INCLUSIVE
-                                            // frontier advances this many tiles per L2 round trip
+#ifndef B200GS_LOOKBACK_WINDOW
+#define B200GS_LOOKBACK_WINDOW 8
+#endif
+constexpr int LOOKBACK_WINDOW = B200GS_LOOKBACK_WINDOW;  // predecessors inspected per step (independent loads in flight): the
+                                                         // INCLUSIVE frontier advances this many tiles per L2 round trip
 
 __device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 __device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
@@ -103,10 +107,12 @@ __device__ __forceinline__ uint32_t lookback_exclusive_warp(uint32_t* __restrict
 	return excl;
 }
 
+// One tile of one radix pass.  `ticket` != nullptr: the tile id is drawn from it (a CTA only ever waits on CTAs that already
+// started); nullptr: tile = blockIdx.x (all CTAs of the grid are co-resident, fused multi-pass kernel below).
 template <int ITEMS>
-__global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(
+__device__ __forceinline__ void onesweep_tile(
 	const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
-	uint32_t* __restrict__ vals_out, int64_t n_max, const unsigned long long* __restrict__ n_dev, int shift, int bits,
+	uint32_t* __restrict__ vals_out, int64_t n, int shift, int bits,
 	const uint32_t* __restrict__ hist /*[256] this pass: produced by the kernel that wrote the keys*/,
 	uint32_t* __restrict__ lookback /*[tiles][256]*/, unsigned int* __restrict__ ticket)
 {
@@ -122,11 +128,8 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(
 	__shared__ int s_trivial;
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	pdl_trigger();
 	for (int i = tid; i < WARPS * 256; i += SORT_THREADS) (&s_warp_hist[0][0])[i] = 0;
-	pdl_wait();
-	const int64_t n = load_count(n_dev, n_max);
-	if (tid == 0) { s_tile = atomicAdd(ticket, 1u); s_trivial = 0; }
+	if (tid == 0) { s_tile = ticket ? atomicAdd(ticket, 1u) : blockIdx.x; s_trivial = 0; }
 	__syncthreads();
 	if ((int64_t)__ldcg(hist + tid) == n && n > 0) s_trivial = 1;  // every key has the same digit: the pass is the identity permutation
 	const uint32_t tile = s_tile;
@@ -217,6 +220,50 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(
 		const uint32_t dst = s_digit_base[d] + (uint32_t)i;
 		keys_out[dst] = k;
 		vals_out[dst] = s_vals[i];
+	}
+}
+
+template <int ITEMS>
+__global__ void __launch_bounds__(SORT_THREADS, ITEMS == SORT_ITEMS_LARGE ? 3 : 6) onesweep_pass_kernel(
+	const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
+	uint32_t* __restrict__ vals_out, int64_t n_max, const unsigned long long* __restrict__ n_dev, int shift, int bits,
+	const uint32_t* __restrict__ hist, uint32_t* __restrict__ lookback, unsigned int* __restrict__ ticket)
+{
+	pdl_trigger();
+	pdl_wait();
+	onesweep_tile<ITEMS>(keys_in, vals_in, keys_out, vals_out, load_count(n_dev, n_max), shift, bits, hist, lookback, ticket);
+}
+
+// All passes of a sort in ONE launch, for grids that are co-resident (one CTA per tile, grid barrier between passes).  At
+// P = 100 k a radix pass is 98 CTAs and ~4 us of SM work inside ~9 us of launch, ramp and drain (ncu: SMs active 40 % of the
+// kernel's duration): four launches paid that four times.
+template <int ITEMS>
+__global__ void __launch_bounds__(SORT_THREADS, ITEMS == SORT_ITEMS_LARGE ? 3 : 6) onesweep_fused_kernel(
+	uint32_t* key_a, uint32_t* key_b, uint32_t* val_a, uint32_t* val_b, int64_t n_max, const unsigned long long* __restrict__ n_dev,
+	int end_bit, const uint32_t* __restrict__ hist /*[passes][256]*/, uint32_t* __restrict__ lookback /*[passes][tiles][256]*/,
+	unsigned int* __restrict__ barrier /*zero on entry*/)
+{
+	pdl_trigger();
+	pdl_wait();
+	const int64_t n = load_count(n_dev, n_max);
+	const int passes = (end_bit + 7) / 8;
+	uint32_t *ki = key_a, *ko = key_b, *vi = val_a, *vo = val_b;
+	for (int p = 0; p < passes; p++) {
+		const int bits = end_bit - 8 * p < 8 ? end_bit - 8 * p : 8;
+		onesweep_tile<ITEMS>(ki, vi, ko, vo, n, 8 * p, bits, hist + 256 * p, lookback + (size_t)p * gridDim.x * 256, nullptr);
+		if (p + 1 < passes) {  // grid barrier: every tile of pass p has been scattered before pass p+1 reads
+			__syncthreads();
+			if (threadIdx.x == 0) {
+				__threadfence();
+				atomicAdd(barrier, 1u);
+				const unsigned target = (unsigned)(p + 1) * gridDim.x;
+				while (ld_volatile(barrier) < target) {}
+				__threadfence();
+			}
+			__syncthreads();
+		}
+		uint32_t* t = ki; ki = ko; ko = t;
+		t = vi; vi = vo; vo = t;
 	}
 }
 
@@ -505,13 +552,40 @@ void launch_finalize_header(GeomState& gs, int64_t capacity, cudaStream_t stream
 }
 int tile_count_stride() { return COUNT_STRIDE; }
 
+// CTAs of the radix pass kernel that are resident at once (occupancy x SM count); a fused multi-pass launch must not exceed it
+static int64_t fused_capacity(int items) {
+	static int64_t cap[2] = {-1, -1};
+	const int k = items == SORT_ITEMS_SMALL ? 0 : 1;
+	if (cap[k] < 0) {
+		static int off = -1;  // B200GS_FUSED_SORT=0: separate launches per pass (A/B)
+		if (off < 0) { const char* e = getenv("B200GS_FUSED_SORT"); off = (e && atoi(e) == 0) ? 1 : 0; }
+		int dev = 0, sms = 0, per_sm = 0;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		if (k == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, onesweep_fused_kernel<SORT_ITEMS_SMALL>, SORT_THREADS, 0);
+		else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, onesweep_fused_kernel<SORT_ITEMS_LARGE>, SORT_THREADS, 0);
+		cap[k] = off ? 0 : (int64_t)per_sm * sms;
+	}
+	return cap[k];
+}
+
 int launch_radix_sort(uint32_t* key_a, uint32_t* key_b, uint32_t* val_a, uint32_t* val_b, int64_t n_max,
                       const unsigned long long* n_dev, int end_bit, uint32_t* hist, uint32_t* lookback,
-                      unsigned int* tickets, cudaStream_t stream) {
+                      unsigned int* tickets, unsigned int* barrier, cudaStream_t stream) {
 	if (n_max <= 0 || end_bit <= 0) return 0;
 	const int passes = (end_bit + 7) / 8;
 	const int items = sort_items_for(n_max);
 	const int64_t tiles = sort_tiles_for(n_max);
+	if (passes > 1 && barrier != nullptr && tiles <= fused_capacity(items)) {  // every tile's CTA fits on the device at once
+		if (items == SORT_ITEMS_SMALL)
+			launch_k(PDL_SORT, onesweep_fused_kernel<SORT_ITEMS_SMALL>, dim3((unsigned)tiles), dim3(SORT_THREADS), stream,
+				key_a, key_b, val_a, val_b, n_max, n_dev, end_bit, (const uint32_t*)hist, lookback, barrier);
+		else
+			launch_k(PDL_SORT, onesweep_fused_kernel<SORT_ITEMS_LARGE>, dim3((unsigned)tiles), dim3(SORT_THREADS), stream,
+				key_a, key_b, val_a, val_b, n_max, n_dev, end_bit, (const uint32_t*)hist, lookback, barrier);
+		count_launch();
+		return passes & 1;
+	}
 	uint32_t *ki = key_a, *ko = key_b, *vi = val_a, *vo = val_b;
 	for (int p = 0; p < passes; p++) {
 		const int bits = end_bit - 8 * p < 8 ? end_bit - 8 * p : 8;
@@ -534,7 +608,7 @@ void launch_depth_order(GeomState& gs, int P, cudaStream_t stream) {
 	if (P <= 0) return;
 	// keys: key_a, values: order (identity), digit histograms gs.hist[0..3]: all written by preprocess; 4 passes -> result in (key_a, order)
 	unsigned int* tickets = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(gs.hdr) + offsetof(GeomHeader, sort_ticket));
-	launch_radix_sort(gs.key_a, gs.key_b, gs.order, gs.val_b, P, nullptr, 32, gs.hist, gs.lookback, tickets, stream);
+	launch_radix_sort(gs.key_a, gs.key_b, gs.order, gs.val_b, P, nullptr, 32, gs.hist, gs.lookback, tickets, &gs.hdr->sort_barrier[0], stream);
 }
 
 void launch_scan_emit(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is, int P, int64_t capacity, cudaStream_t stream, bool chained) {
@@ -562,7 +636,7 @@ void launch_tile_sort(const b200gs_view_t& v, GeomState& gs, BinningState& bs, i
 	const unsigned long long* n_dev = &gs.hdr->num_rendered;
 	unsigned int* tickets = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(gs.hdr) + offsetof(GeomHeader, sort_ticket)) + 4;
 	const int where = launch_radix_sort(bs.key_a, bs.key_b, bs.val_a, bs.val_b, capacity, n_dev, bit, gs.hist + 4 * 256,
-	                                    bs.lookback, tickets, stream);
+	                                    bs.lookback, tickets, &gs.hdr->sort_barrier[1], stream);
 	bs.sorted_keys = where ? bs.key_b : bs.key_a;
 	bs.sorted_vals = where ? bs.val_b : bs.val_a;
 }

@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32) blend_forward_kernel(
 	if (blockIdx.x == 0 && threadIdx.x < 8) hdr->sort_ticket[threadIdx.x] = 0u;
 	if (blockIdx.x == 0 && threadIdx.x == 8) {
 		hdr->scan_ticket = 0u; hdr->ranges_done = 0u; hdr->emit_done = 0u; hdr->num_acc = 0ull; hdr->prefilter_violation = 0u;
+		hdr->sort_barrier[0] = 0u; hdr->sort_barrier[1] = 0u;
 	}
 
 	for (uint32_t unit = tk.next(lane); unit < units; unit = tk.next(lane)) {

@@ -31,7 +31,8 @@ struct GeomHeader {  // first 256 bytes of the geom workspace
 	unsigned int blend_exit[2];       // warps that have run dry; the last one re-arms ticket and counter
 	unsigned long long num_acc;       // instance count accumulated by the preprocess kernel (num_rendered is assigned from the scan)
 	unsigned int prefilter_violation; // 2 when a Gaussian was culled although `prefiltered` was set
-	unsigned int pad[43];
+	unsigned int sort_barrier[2];     // grid barriers of the fused multi-pass sorts (depth, tile)
+	unsigned int pad[41];
 };
 static_assert(sizeof(GeomHeader) == 256, "header size");
 
@@ -103,7 +104,8 @@ void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, u
 // holds the result (0: a, 1: b).
 int launch_radix_sort(uint32_t* key_a, uint32_t* key_b, uint32_t* val_a, uint32_t* val_b, int64_t n_max,
                       const unsigned long long* n_dev, int end_bit, uint32_t* hist /*[passes][256]*/,
-                      uint32_t* lookback, unsigned int* tickets, cudaStream_t stream);
+                      uint32_t* lookback, unsigned int* tickets, unsigned int* barrier /*zero on entry, or nullptr: one launch per pass*/,
+                      cudaStream_t stream);
 bool tile_counts_path(int tiles);  // scan_emit also produces tile ranges + blend schedule (small tile grids)
 int tile_count_stride();
 void launch_depth_order(GeomState& gs, int P, cudaStream_t stream);                     // stable sort of Gaussian ids by depth bits

@@ -169,7 +169,10 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(
 	__shared__ __align__(16) float s_opac[PRE_THREADS];
 	__shared__ __align__(16) float s_conf[PRE_THREADS];
 	__shared__ __align__(16) float s_feat[PRE_THREADS * 3];     // language_feature_precomp or shs_language
-	__shared__ __align__(128) float4 s_rec[PRE_THREADS * 4];    // outgoing splat records
+	// outgoing splat records: staged in the SH buffer once every thread is done with its coefficients (8 KB less shared
+	// memory = 6 instead of 5 CTAs per SM: the 782 CTAs of the 100 k-Gaussian shape then fit ONE wave of 888 slots instead of
+	// one and a 6 % tail wave, which had doubled the kernel's latency-bound duration)
+	float4* s_rec = reinterpret_cast<float4*>(s_sh);
 	__shared__ __align__(8) uint64_t s_bar;
 	const int li = threadIdx.x;
 	pdl_trigger();
@@ -336,6 +339,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(
 		if ((li & 31) == 0 && wsum) atomicAdd(&s_instances, (unsigned long long)wsum);
 	}
 	// splat records leave the CTA as one contiguous bulk store
+	__syncthreads();  // every thread has read its SH row / colour: the buffer is free for the records
 	s_rec[4 * li] = r0; s_rec[4 * li + 1] = r1; s_rec[4 * li + 2] = r2; s_rec[4 * li + 3] = r3;
 	tma_store_fence();
 	__syncthreads();
@@ -389,7 +393,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_backward_kernel(
 	// inputs staged as in the forward; the same buffers are reused for the outgoing gradients (a thread only ever
 	// touches its own row), which leave as contiguous bulk stores instead of 12/24/192-byte strided scalar stores
 	__shared__ __align__(128) float s_sh[PRE_THREADS * 48];     // SH in -> dL/dSH out
-	__shared__ __align__(128) float4 s_grec[PRE_THREADS * 4];
+	__shared__ __align__(128) float4 s_grec[PRE_THREADS * 4];   // (read straight from global it cost +35 % at 6 M Gaussians: 16-byte loads of 64-byte rows)
 	__shared__ __align__(16) float s_means[PRE_THREADS * 3];    // means in -> dL/dmeans3D out
 	__shared__ __align__(16) float s_geo[PRE_THREADS * 7];      // scales+rotations / cov3D in -> dL/dscales / dL/dcov3D out
 	__shared__ __align__(16) float s_feat[PRE_THREADS * 3];     // feature / language SH in -> their gradient out
