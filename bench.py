@@ -214,10 +214,12 @@ def e2e_b200gs(args, wl, rank, world, dev):
     are uploaded from pinned host memory (b200gs.hostio.PinnedFeeder: one copy per step on a copy stream, step i+1's upload
     overlapping step i's kernels) and the step's result is read back.  Returns (views/s, seconds, H2D bytes per step)."""
     from b200gs import rasterizer as rz
-    from b200gs.hostio import PinnedFeeder
+    from b200gs.hostio import PinnedFeeder, ResultReader
     from diff_gaussian_rasterization import GaussianRasterizer
     P, ext, nviews = wl.scene.P, wl.extended, len(wl.cams)
     feeder = PinnedFeeder(wl.host, dev)
+    # every step's result is copied back inside the loop; the host picks it up `lag` steps later (0: stall per step, as `.item()`)
+    reader = ResultReader(lag=int(os.environ.get("B200GS_E2E_LAG", "1")))
     settings = [wl.settings(cam, P) for cam in wl.cams]
 
     def body(vi, t):
@@ -229,7 +231,8 @@ def e2e_b200gs(args, wl, rank, world, dev):
         if args.fwd_only:
             with torch.no_grad():
                 outs = GaussianRasterizer(settings[vi])(**kw)
-            return float(outs[0].sum().item())
+            reader.push(outs[0].sum())
+            return reader.pop()
         outs = GaussianRasterizer(settings[vi])(**kw)
         cot = wl.cot[vi]
         # the loss lives outside the rasterizer: its gradient w.r.t. the rendered maps is handed to autograd directly
@@ -237,7 +240,8 @@ def e2e_b200gs(args, wl, rank, world, dev):
         if world > 1:
             g = torch.cat([t[k].grad.reshape(-1) for k in sorted(t)])
             dist.all_reduce(g)
-        return float(outs[0].sum().item())  # the step's result read back to the host
+        reader.push(outs[0].sum())  # the step's result: device -> pinned host copy enqueued now ...
+        return reader.pop()         # ... and consumed one step later (no per-step host stall)
 
     def step(i):
         t = {k: v.requires_grad_(True) for k, v in feeder.next().items()}
@@ -248,7 +252,9 @@ def e2e_b200gs(args, wl, rank, world, dev):
 
     rz.set_binning_capacity("auto")  # public knob: learned capacity, no host sync inside the forward after the first call
     try:
-        sec = wall_loop(args.steps, max(3, args.warmup), step, world)
+        sec = wall_loop(args.steps, max(3, args.warmup), step, world)  # ends with a device synchronize: every copy has landed
+        last = reader.drain()
+        assert all(np.isfinite(v) for v in last)
         rz._check_pending(block=True)
     finally:
         rz.set_binning_capacity(None)
@@ -585,7 +591,8 @@ def run_b200gs(args, rank, world, local):
                              h2d_bytes_per_step=feeder_bytes, d2h_bytes_per_step=4 + 16,
                              path="diff_gaussian_rasterization.GaussianRasterizer + torch.autograd.backward (binning capacity 'auto'); "
                                   "every step's parameters are uploaded from pinned host memory (b200gs.hostio.PinnedFeeder: one copy per "
-                                  "step on a copy stream, step i+1's upload overlapping step i's kernels); color.sum().item() read back"),
+                                  "step on a copy stream, step i+1's upload overlapping step i's kernels); color.sum() copied back to pinned host "
+                                  "memory every step and consumed one step later (b200gs.hostio.ResultReader)"),
                     gpu_launches=int(launches_per_step * args.steps), gpu_launches_per_step=int(launches_per_step),
                     clocks=clocks, roofline=roofline, cpu_baseline=cpu, vanilla=vanilla, train=train, impl="b200gs",
                     collective_check=coll, wall_s=wall, **extras)

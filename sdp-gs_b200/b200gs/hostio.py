@@ -79,3 +79,43 @@ class PinnedFeeder:
         self.released[self._last].record(cs)
         if not self.prefetch:
             self._enqueue_copy(self.cur)
+
+
+class ResultReader:
+    """Device -> host read-back of one scalar per step without stalling the step that produced it.
+
+    `push(t)` enqueues, on the current stream, the copy of the 1-element tensor `t` into a pinned slot and records an event;
+    `pop()` returns the oldest value still in flight once more than `lag` results are pending (it waits for THAT result's
+    event only, so the host is already enqueueing step i+1 while step i executes); `drain()` returns the rest.  Every step's
+    result still crosses the bus, inside the loop that produced it -- only the per-step host stall of `.item()` is gone
+    (the reference's loop has it: `loss.item()` every iteration, train.py:197)."""
+
+    def __init__(self, lag: int = 1, slots: int = 8):
+        self.lag = int(lag)
+        self.host = torch.empty((slots,), dtype=torch.float32).pin_memory()
+        self.events = [torch.cuda.Event() for _ in range(slots)]
+        self.head = self.tail = 0
+
+    def push(self, t):
+        n = len(self.events)
+        assert self.head - self.tail < n, "ResultReader: too many results in flight"
+        i = self.head % n
+        with torch.no_grad():
+            self.host[i:i + 1].copy_(t.detach().reshape(1).float(), non_blocking=True)
+        self.events[i].record()
+        self.head += 1
+
+    def _take(self):
+        i = self.tail % len(self.events)
+        self.events[i].synchronize()
+        self.tail += 1
+        return float(self.host[i])
+
+    def pop(self):
+        return self._take() if self.head - self.tail > self.lag else None
+
+    def drain(self):
+        out = []
+        while self.head > self.tail:
+            out.append(self._take())
+        return out

@@ -144,6 +144,28 @@ def _build_view(rs, P, M, extended, keep):
     return v
 
 
+_VIEW_CACHE = {}  # (id(settings), M, extended) -> (settings, View, tensors kept alive)
+
+
+def _cached_view(rs, P, M, extended, keep):
+    """The View struct of a settings tuple is a pure function of it (pointers of its four tensors + scalars): built once per
+    settings object instead of once per forward and once per backward (the tuple is immutable; its tensors may be updated in
+    place, the pointers stay valid).  Not cached when a tensor had to be converted (the struct would point at a private copy)."""
+    key = (id(rs), M, extended)
+    hit = _VIEW_CACHE.get(key)
+    if hit is not None and hit[0] is rs:
+        return hit[1]
+    mine = []
+    v = _build_view(rs, P, M, extended, mine)
+    if all(a is b for a, b in zip(mine, (rs.bg, rs.viewmatrix, rs.projmatrix, rs.campos))):
+        if len(_VIEW_CACHE) > 512:
+            _VIEW_CACHE.clear()
+        _VIEW_CACHE[key] = (rs, v, mine)
+    else:
+        keep.extend(mine)
+    return v
+
+
 def _forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, shs_language,
                   language_feature_precomp, confidence, extended):
     if means3D.dim() != 2 or means3D.shape[1] != 3:
@@ -167,15 +189,15 @@ def _forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations,
     g.means3D, g.shs, g.colors_precomp, g.opacities = _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(opacities)
     g.scales, g.rotations, g.cov3D_precomp = _ptr(scales), _ptr(rotations), _ptr(cov3Ds_precomp)
     g.language_feature_precomp, g.shs_language, g.confidence = _ptr(language_feature_precomp), _ptr(shs_language), _ptr(confidence)
-    v = _build_view(rs, P, M, extended, keep)
+    v = _cached_view(rs, P, M, extended, keep)
 
     f32 = dict(dtype=torch.float32, device=dev)
     radii = torch.empty((P,), dtype=torch.int32, device=dev)
     depth = alpha = feature = None
     o = Outputs()
-    if extended:  # one allocation for the four maps
-        shapes = ((3, H, W), (1, H, W), (1, H, W), (3, H, W))
-        color, depth, alpha, feature = _carve(torch.empty((_carve_size(shapes),), **f32), shapes)
+    if extended:  # one allocation for the four maps: eight consecutive planes
+        planes = torch.empty((8, H, W), **f32)
+        color, depth, alpha, feature = planes[0:3], planes[3:4], planes[4:5], planes[5:8]
         o.depth, o.alpha, o.feature = depth.data_ptr(), alpha.data_ptr(), feature.data_ptr()
     else:
         color = torch.empty((3, H, W), **f32)
@@ -247,7 +269,7 @@ def _backward_impl(rs, num_rendered, capacity, extended, means3D, sh, colors_pre
     g.means3D, g.shs, g.colors_precomp, g.opacities = _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(opacities)
     g.scales, g.rotations, g.cov3D_precomp = _ptr(scales), _ptr(rotations), _ptr(cov3Ds_precomp)
     g.language_feature_precomp, g.shs_language, g.confidence = _ptr(language_feature_precomp), _ptr(shs_language), _ptr(confidence)
-    v = _build_view(rs, P, M, extended, keep)
+    v = _cached_view(rs, P, M, extended, keep)
     ws = Workspace()
     ws.geom, ws.geom_bytes, ws.image, ws.image_bytes = geom.data_ptr(), geom.numel(), img.data_ptr(), img.numel()
     ws.binning, ws.binning_bytes = binning.data_ptr(), binning.numel()
@@ -360,13 +382,20 @@ def capture_graph(fn, device, warmup=None):
             (warmup or fn)()
         torch.cuda.synchronize(device)
         _WARMED.add(key)
+    import gc
     g = torch.cuda.CUDAGraph()
-    with torch.cuda.stream(side):
-        g.capture_begin()
-        try:
-            fn()
-        finally:
-            g.capture_end()
+    gc_was_on = gc.isenabled()
+    gc.disable()  # a collection inside the capture could destroy an old CUDA graph, which invalidates a global-mode capture
+    try:
+        with torch.cuda.stream(side):
+            g.capture_begin(capture_error_mode="relaxed")
+            try:
+                fn()
+            finally:
+                g.capture_end()
+    finally:
+        if gc_was_on:
+            gc.enable()
     torch.cuda.current_stream(device).wait_stream(side)
     return g
 
