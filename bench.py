@@ -48,7 +48,7 @@ STAGES = ["memset", "preprocess", "depth_sort", "scan", "duplicate", "tile_sort"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200gs", choices=["b200gs", "reference"])
     ap.add_argument("--workload", default="llff_fern_3view")

@@ -113,6 +113,7 @@ def _cpu_deep_copy_tuple(args):
 
 
 _WS_BYTES = {}
+_BIN_BYTES = {}
 
 
 def _ws_bytes(P, W, H):
@@ -226,12 +227,17 @@ def _forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations,
         if auto_key is not None:
             _AUTO[auto_key] = int(n.value * 1.3) + 4096
             auto_key = None  # exact this time, nothing to verify
-    else:
-        check(lib.b200gs_forward_preprocess(C.byref(v), C.byref(g), C.byref(o), C.byref(ws), stream, None))
+        binning = torch.empty((lib.b200gs_binning_bytes(capacity),), dtype=torch.uint8, device=dev)
+        ws.binning, ws.binning_bytes = binning.data_ptr(), binning.numel()
+        check(lib.b200gs_forward_render(C.byref(v), C.byref(g), C.byref(o), C.byref(ws), C.c_int64(capacity), stream))
+    else:  # capacity known up front: one call, no host synchronization
         num_rendered, capacity = -1, int(_AUTO[auto_key] if auto_key is not None else _CAPACITY)
-    binning = torch.empty((lib.b200gs_binning_bytes(capacity),), dtype=torch.uint8, device=dev)
-    ws.binning, ws.binning_bytes = binning.data_ptr(), binning.numel()
-    check(lib.b200gs_forward_render(C.byref(v), C.byref(g), C.byref(o), C.byref(ws), C.c_int64(capacity), stream))
+        bb = _BIN_BYTES.get(capacity)
+        if bb is None:
+            bb = _BIN_BYTES[capacity] = int(lib.b200gs_binning_bytes(capacity))
+        binning = torch.empty((bb,), dtype=torch.uint8, device=dev)
+        ws.binning, ws.binning_bytes = binning.data_ptr(), bb
+        check(lib.b200gs_forward(C.byref(v), C.byref(g), C.byref(o), C.byref(ws), C.c_int64(capacity), stream))
     if auto_key is not None:  # asynchronous read-back of {num_rendered, overflow}; looked at by a later call
         ev, host = _FREE_STATUS.pop() if _FREE_STATUS else (torch.cuda.Event(), torch.empty((16,), dtype=torch.uint8, pin_memory=True))
         host.copy_(geom[:16], non_blocking=True)

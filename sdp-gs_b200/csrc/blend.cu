@@ -158,8 +158,11 @@ struct Ticket {
 	}
 };
 
+#ifndef B200GS_FWD_MIN_CTAS
+#define B200GS_FWD_MIN_CTAS 1
+#endif
 template <bool EXT>
-__global__ void __launch_bounds__(BLEND_WARPS * 32) blend_forward_kernel(
+__global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_FWD_MIN_CTAS) blend_forward_kernel(
 	const uint2* ranges, const uint32_t* order, const uint32_t* point_list, const float4* rec,
 	int W, int H, int grid_x, uint32_t units, GeomHeader* hdr, uint4* clean_words, size_t clean_count,
 	const float* __restrict__ bg, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,

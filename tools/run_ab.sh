@@ -1,6 +1,6 @@
-for lag in 0 1 2; do
-B200GS_E2E_LAG=$lag timeout 600 python bench.py --steps 60 --warmup 5 --no-extras --no-cpu-baseline --no-train 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('lag $lag: ms_per_step', round(d['ms_per_step'],4), 'e2e', round(d['e2e']['ms_per_step'],4), 'vanilla e2e', round(d['vanilla']['e2e']['ms_per_step'],4))"
+timeout 300 python tools/stage_times.py 2>gpurun_out/r2_st.err | tee gpurun_out/r2_st_default.json
+for v in f7 f8; do
+  B200GS_LIB=$PWD/variants/libb200gs_$v.so timeout 300 python tools/stage_times.py 2>/dev/null | tee gpurun_out/r2_st_$v.json
+  B200GS_LIB=$PWD/variants/libb200gs_$v.so timeout 600 python tools/stage_times.py --workload stress_train --steps 5 --views 2 2>/dev/null | tee gpurun_out/r2_st_stress_$v.json
 done
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 600 python tools/profile_e2e.py 2>&1 | grep -E "ms/step"
