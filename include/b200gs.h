@@ -149,7 +149,8 @@ const char* b200gs_last_error(void);
 
 size_t b200gs_geom_bytes(int32_t P);
 size_t b200gs_image_bytes(int32_t width, int32_t height);
-size_t b200gs_binning_bytes(int64_t capacity); /* capacity = max number of (Gaussian,tile) instances, < 2^30 */
+size_t b200gs_binning_bytes(int64_t capacity, int32_t width, int32_t height); /* capacity = max number of (Gaussian,tile)
+                                                  instances, < 2^30; the image size enters through the per-block survivor bitmap */
 size_t b200gs_scratch_bytes(int32_t P);
 
 /* One-time initialisation of persistent workspaces (see b200gs_workspace_t.persistent): zeroes the geom workspace's
@@ -165,7 +166,7 @@ int b200gs_forward_preprocess(const b200gs_view_t* view, const b200gs_gaussians_
                               const b200gs_workspace_t* ws, void* stream, int64_t* num_rendered_host);
 
 /* Stage 2: duplicate-with-keys, tile sort, tile ranges, blend.  ws->binning must hold
- * b200gs_binning_bytes(capacity) bytes.  If the device-side instance count exceeds `capacity`
+ * b200gs_binning_bytes(capacity, width, height) bytes.  If the device-side instance count exceeds `capacity`
  * the overflow flag is raised (see b200gs_forward_status) and the surplus instances are dropped. */
 int b200gs_forward_render(const b200gs_view_t* view, const b200gs_gaussians_t* g, const b200gs_outputs_t* out,
                           const b200gs_workspace_t* ws, int64_t capacity, void* stream);

@@ -105,7 +105,7 @@ def _load():
         getattr(lib, f).restype = C.c_size_t
     lib.b200gs_geom_bytes.argtypes = [C.c_int32]
     lib.b200gs_image_bytes.argtypes = [C.c_int32, C.c_int32]
-    lib.b200gs_binning_bytes.argtypes = [C.c_int64]
+    lib.b200gs_binning_bytes.argtypes = [C.c_int64, C.c_int32, C.c_int32]
     lib.b200gs_scratch_bytes.argtypes = [C.c_int32]
     lib.b200gs_launch_count.restype = C.c_int64
     P = C.POINTER

@@ -227,14 +227,14 @@ def _forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations,
         if auto_key is not None:
             _AUTO[auto_key] = int(n.value * 1.3) + 4096
             auto_key = None  # exact this time, nothing to verify
-        binning = torch.empty((lib.b200gs_binning_bytes(capacity),), dtype=torch.uint8, device=dev)
+        binning = torch.empty((lib.b200gs_binning_bytes(capacity, W, H),), dtype=torch.uint8, device=dev)
         ws.binning, ws.binning_bytes = binning.data_ptr(), binning.numel()
         check(lib.b200gs_forward_render(C.byref(v), C.byref(g), C.byref(o), C.byref(ws), C.c_int64(capacity), stream))
     else:  # capacity known up front: one call, no host synchronization
         num_rendered, capacity = -1, int(_AUTO[auto_key] if auto_key is not None else _CAPACITY)
-        bb = _BIN_BYTES.get(capacity)
+        bb = _BIN_BYTES.get((capacity, W, H))
         if bb is None:
-            bb = _BIN_BYTES[capacity] = int(lib.b200gs_binning_bytes(capacity))
+            bb = _BIN_BYTES[(capacity, W, H)] = int(lib.b200gs_binning_bytes(capacity, W, H))
         binning = torch.empty((bb,), dtype=torch.uint8, device=dev)
         ws.binning, ws.binning_bytes = binning.data_ptr(), bb
         check(lib.b200gs_forward(C.byref(v), C.byref(g), C.byref(o), C.byref(ws), C.c_int64(capacity), stream))
@@ -451,7 +451,7 @@ class RasterSession:
         u8 = dict(dtype=torch.uint8, device=dev)
         self.geom = torch.empty((lib.b200gs_geom_bytes(P),), **u8)
         self.img = torch.empty((lib.b200gs_image_bytes(W, H),), **u8)
-        self.binning = torch.empty((lib.b200gs_binning_bytes(self.capacity),), **u8)
+        self.binning = torch.empty((lib.b200gs_binning_bytes(self.capacity, W, H),), **u8)
         ws = self.ws = Workspace()
         ws.geom, ws.geom_bytes, ws.image, ws.image_bytes = self.geom.data_ptr(), self.geom.numel(), self.img.data_ptr(), self.img.numel()
         ws.binning, ws.binning_bytes = self.binning.data_ptr(), self.binning.numel()

@@ -137,8 +137,10 @@ BinningState binning_from_chunk(char* base, int W, int H, int64_t capacity) {
 	BinningState b;
 	char* p = base;
 	const size_t n = (size_t)(capacity > 0 ? capacity : 1);
-	(void)W; (void)H;
+	const size_t tiles = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
+	b.surv_words = n / 32 + tiles + 2;
 	carve(p, b.lookback, (size_t)4 * sort_tiles_for(capacity) * 256);  // up to 4 tile passes (bit <= 32)
+	carve(p, b.surv_bits, 8 * b.surv_words);
 	carve(p, b.key_a, n);
 	carve(p, b.key_b, n);
 	carve(p, b.val_a, n);
@@ -210,7 +212,7 @@ void b200gs_abi_sizes(int64_t* out6) {
 
 size_t b200gs_geom_bytes(int32_t P) { return geom_from_chunk(nullptr, P).bytes; }
 size_t b200gs_image_bytes(int32_t width, int32_t height) { return image_from_chunk(nullptr, width, height).bytes; }
-size_t b200gs_binning_bytes(int64_t capacity) { return binning_from_chunk(nullptr, 0, 0, capacity).bytes; }
+size_t b200gs_binning_bytes(int64_t capacity, int32_t width, int32_t height) { return binning_from_chunk(nullptr, width, height, capacity).bytes; }
 size_t b200gs_scratch_bytes(int32_t P) { return (size_t)(P > 0 ? P : 1) * GREC_FLOATS * sizeof(float); }
 
 void b200gs_geom_layout(int32_t P, int64_t* off) {
@@ -286,7 +288,7 @@ static int forward_render_impl(const b200gs_view_t* v, const b200gs_gaussians_t*
 	if (v->extended && (!out->depth || !out->alpha || !out->feature)) return fail(B200GS_E_ARG, "extended outputs are required");
 	if (capacity < 0) return fail(B200GS_E_ARG, "negative capacity");
 	if (capacity >= (1ll << 30)) return fail(B200GS_E_ARG, "capacity exceeds 2^30 instances (30-bit look-back counters)");
-	if (!ws->binning || ws->binning_bytes < b200gs_binning_bytes(capacity)) return fail(B200GS_E_ARG, "binning workspace too small");
+	if (!ws->binning || ws->binning_bytes < b200gs_binning_bytes(capacity, v->width, v->height)) return fail(B200GS_E_ARG, "binning workspace too small");
 	cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
 	const int P = g->P;
 	GeomState gs = geom_from_chunk(reinterpret_cast<char*>(ws->geom), P);
@@ -355,7 +357,7 @@ int b200gs_backward(const b200gs_view_t* v, const b200gs_gaussians_t* g, const i
 		if (!g->shs || v->sh_coeffs != 16 || !g->scales || !g->rotations)
 			return fail(B200GS_E_ARG, "gradient scatter needs shs with 16 coefficients and the scales/rotations path");
 	}
-	if (!ws->binning || ws->binning_bytes < b200gs_binning_bytes(capacity)) return fail(B200GS_E_ARG, "binning workspace too small");
+	if (!ws->binning || ws->binning_bytes < b200gs_binning_bytes(capacity, v->width, v->height)) return fail(B200GS_E_ARG, "binning workspace too small");
 	cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
 	GeomState gs = geom_from_chunk(reinterpret_cast<char*>(ws->geom), P);
 	ImageState is = image_from_chunk(reinterpret_cast<char*>(ws->image), v->width, v->height);

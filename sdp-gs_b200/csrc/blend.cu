@@ -60,6 +60,7 @@ template <int N>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct Unit {
+	uint32_t tile, sub;
 	unsigned px, py;
 	bool inside;
 	float pxf, pyf;
@@ -70,8 +71,8 @@ struct Unit {
 __device__ __forceinline__ Unit make_unit(uint32_t unit, const uint32_t* order, const uint2* ranges, int W, int H, int grid_x) {
 	Unit u;
 	const unsigned lane = threadIdx.x & 31;
-	const uint32_t tile = __ldcg(order + (unit >> 3));
-	const unsigned sub = unit & 7;
+	const uint32_t tile = u.tile = __ldcg(order + (unit >> 3));
+	const unsigned sub = u.sub = unit & 7;
 	const unsigned tx = tile % grid_x, ty = tile / grid_x;
 	const unsigned bx = tx * TILE_X + (sub & 1) * 8, by = ty * TILE_Y + (sub >> 1) * 4;
 	u.px = bx + (lane & 7);
@@ -118,11 +119,14 @@ struct Walk {
 	__device__ __forceinline__ void load_geo(uint32_t id, float4& g0, float4& g1) const {
 		if (id != NOID) { const float4* p = rec + 4 * (size_t)id; g0 = __ldca(p); g1 = __ldca(p + 1); }
 	}
-	// cull round r; survivors go to ring slots head.. in walk order, their payload copies are issued
+	// cull round r; survivors go to ring slots head.. in walk order, their payload copies are issued.  The round's survivor
+	// mask is left in `bits[r]` for the backward (BinningState::surv_bits).
 	template <bool EXT, bool WITH_ID, typename S>
-	__device__ __forceinline__ int stage(S& s, int r, uint32_t id, const float4 g0, const float4 g1, const PixelBlock& pb, int head) const {
+	__device__ __forceinline__ int stage(S& s, int r, uint32_t id, const float4 g0, const float4 g1, const PixelBlock& pb, int head,
+	                                     uint32_t* bits) const {
 		const bool keep = id != NOID && !cull_block(g0, g1, pb);
 		const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+		if (lane == 0) bits[r] = m;
 		if (m == 0u) return 0;
 		if (keep) {
 			const int slot = (head + __popc(m & ((1u << lane) - 1u))) & (RING - 1);
@@ -159,12 +163,13 @@ struct Ticket {
 };
 
 #ifndef B200GS_FWD_MIN_CTAS
-#define B200GS_FWD_MIN_CTAS 1
+#define B200GS_FWD_MIN_CTAS 6
 #endif
 template <bool EXT>
 __global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_FWD_MIN_CTAS) blend_forward_kernel(
 	const uint2* ranges, const uint32_t* order, const uint32_t* point_list, const float4* rec,
 	int W, int H, int grid_x, uint32_t units, GeomHeader* hdr, uint4* clean_words, size_t clean_count,
+	uint32_t* surv_bits, size_t surv_words,
 	const float* __restrict__ bg, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
 	float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_alpha, float* __restrict__ out_feat)
 {
@@ -192,6 +197,7 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_FWD_MIN_CTAS) blend_f
 		Walk<true> wk;
 		wk.list = point_list + u.range.x; wk.rec = rec; wk.n = (int)(u.range.y - u.range.x); wk.top = 0; wk.lane = lane;
 		const int R = (wk.n + 31) >> 5;
+		uint32_t* bits = surv_bits + (size_t)u.sub * surv_words + (u.range.x >> 5) + u.tile;  // this unit's survivor-bitmap words
 
 		bool done = !u.inside;
 		float T = 1.0f;
@@ -275,7 +281,7 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_FWD_MIN_CTAS) blend_f
 					all_done = __all_sync(0xFFFFFFFFu, done);
 					if (all_done) break;
 				}
-				head += wk.template stage<EXT, false>(S, r, ida, ga0, ga1, u.pb, head);
+				head += wk.template stage<EXT, false>(S, r, ida, ga0, ga1, u.pb, head, bits);
 				cp_commit();
 #pragma unroll
 				for (int j = K_INFLIGHT; j > 0; j--) hist[j] = hist[j - 1];
@@ -327,6 +333,7 @@ template <bool EXT>
 __global__ void __launch_bounds__(BLEND_WARPS * 32) blend_backward_kernel(
 	const uint2* ranges, const uint32_t* order, const uint32_t* point_list, const float4* rec,
 	int W, int H, int grid_x, uint32_t units, unsigned int* ticket, unsigned int* exits,
+	const uint32_t* surv_bits, size_t surv_words,
 	const float* __restrict__ bg, const float* final_T, const uint32_t* n_contrib, const float* __restrict__ dL_dcolor,
 	const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dalpha_map, const float* __restrict__ dL_dfeat,
 	float* __restrict__ grec)
@@ -397,7 +404,7 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32) blend_backward_kernel(
 					const float dx = __fsub_rn(a.x, u.pxf), dy = __fsub_rn(a.y, u.pyf);
 					const float power = pair_power(dx, dy, a.z, a.w, b.x);
 					op[k] = b.y;
-					Gk[k] = expf(power);
+					Gk[k] = exp_fast(power);
 					al[k] = fminf(0.99f, __fmul_rn(b.y, Gk[k]));
 					act[k] = (S.pos[base + k0 + k] <= last_contributor) && !(power > 0.0f) && !(al[k] < 1.0f / 255.0f);
 				}
@@ -468,33 +475,56 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32) blend_backward_kernel(
 			__syncwarp();
 		};
 
-		float4 ga0, ga1, gb0, gb1;
-		ga0 = ga1 = gb0 = gb1 = make_float4(0.f, 0.f, 0.f, 0.f);
-		uint32_t ida = wk.load_id(0), idb = wk.load_id(1), idc = wk.load_id(2);
-		wk.load_geo(ida, ga0, ga1);
-		wk.load_geo(idb, gb0, gb1);
+		// The walk: the forward left, for every round it staged, the ballot of its cull (survivor bitmap), so an entry is neither
+		// fetched nor culled again here: lanes read their bit and their id two rounds ahead, and survivors have their whole
+		// 64-byte record copied into the ring by cp.async.
+		const uint32_t* bits = surv_bits + (size_t)u.sub * surv_words + (u.range.x >> 5) + u.tile;
+		auto load_entry = [&](int r, uint32_t& id) {  // id of walk entry 32 r + lane, NOID when it did not survive (or is past the end)
+			const int i = 32 * r + (int)lane;
+			id = NOID;
+			if (i < wk.n) {
+				const int p = wk.top - i;
+				if ((__ldcg(bits + (p >> 5)) >> (p & 31)) & 1u) id = __ldcg(wk.list + p);
+			}
+		};
+		auto stage = [&](int r, uint32_t id, int hd) -> int {
+			const unsigned m = __ballot_sync(0xFFFFFFFFu, id != NOID);
+			if (m == 0u) return 0;
+			if (id != NOID) {
+				const int slot = (hd + __popc(m & ((1u << lane) - 1u))) & (RING - 1);
+				const float4* src = rec + 4 * (size_t)id;
+				cp_async16(&S.g0[slot], src);
+				cp_async16(&S.g1[slot], src + 1);
+				cp_async16(&S.g2[slot], src + 2);
+				if (EXT) cp_async16(&S.g3[slot], src + 3);
+				S.pos[slot] = (uint32_t)(wk.top - (32 * r + (int)lane) + 1);
+				S.id[slot] = id;
+			}
+			return __popc(m);
+		};
+		uint32_t ida, idb;
+		load_entry(0, ida);
+		load_entry(1, idb);
 		int head = 0, tail = 0;
 		int hist[K_INFLIGHT + 1];
 #pragma unroll
 		for (int j = 0; j <= K_INFLIGHT; j++) hist[j] = 0;
 		__syncwarp();  // basis visible
 		for (int r = 0; r < R; r++) {
-			const uint32_t idd = wk.load_id(r + 3);
-			float4 gc0 = make_float4(0.f, 0.f, 0.f, 0.f), gc1 = gc0;
-			wk.load_geo(idc, gc0, gc1);
+			uint32_t idc;
+			load_entry(r + 2, idc);
 			cp_wait<K_INFLIGHT>();
 			if (hist[K_INFLIGHT] - tail >= BATCH || head - tail > RING - 32) {
 				if (head - tail > RING - 32) { cp_wait<0>(); hist[K_INFLIGHT] = head; }
 				__syncwarp();
 				do { process(tail & (RING - 1), BATCH, BATCH); tail += BATCH; } while (hist[K_INFLIGHT] - tail >= BATCH);
 			}
-			head += wk.template stage<EXT, true>(S, r, ida, ga0, ga1, u.pb, head);
+			head += stage(r, ida, head);
 			cp_commit();
 #pragma unroll
 			for (int j = K_INFLIGHT; j > 0; j--) hist[j] = hist[j - 1];
 			hist[0] = head;
-			ga0 = gb0; ga1 = gb1; gb0 = gc0; gb1 = gc1;
-			ida = idb; idb = idc; idc = idd;
+			ida = idb; idb = idc;
 		}
 		cp_wait<0>();
 		if (head > tail) {
@@ -571,7 +601,7 @@ void launch_blend_forward(const b200gs_view_t& v, GeomState& gs, BinningState& b
 		const unsigned want = (units + BLEND_WARPS - 1) / BLEND_WARPS;
 		launch_blend(PDL_BLEND_FWD, blend_forward_kernel<true>, want < cap ? want : cap, smem, stream, (const uint2*)is.ranges,
 			(const uint32_t*)is.tile_order, (const uint32_t*)bs.sorted_vals, (const float4*)gs.rec,
-			v.width, v.height, gx, units, gs.hdr, clean_words, clean_count, v.background, is.final_T, is.n_contrib, out.color, out.depth, out.alpha, out.feature);
+			v.width, v.height, gx, units, gs.hdr, clean_words, clean_count, bs.surv_bits, bs.surv_words, v.background, is.final_T, is.n_contrib, out.color, out.depth, out.alpha, out.feature);
 	} else {
 		static unsigned cap = 0;
 		constexpr size_t smem = BLEND_WARPS * sizeof(FwdSmem<false>);
@@ -579,7 +609,7 @@ void launch_blend_forward(const b200gs_view_t& v, GeomState& gs, BinningState& b
 		const unsigned want = (units + BLEND_WARPS - 1) / BLEND_WARPS;
 		launch_blend(PDL_BLEND_FWD, blend_forward_kernel<false>, want < cap ? want : cap, smem, stream, (const uint2*)is.ranges,
 			(const uint32_t*)is.tile_order, (const uint32_t*)bs.sorted_vals, (const float4*)gs.rec,
-			v.width, v.height, gx, units, gs.hdr, clean_words, clean_count, v.background, is.final_T, is.n_contrib, out.color, (float*)nullptr, (float*)nullptr, (float*)nullptr);
+			v.width, v.height, gx, units, gs.hdr, clean_words, clean_count, bs.surv_bits, bs.surv_words, v.background, is.final_T, is.n_contrib, out.color, (float*)nullptr, (float*)nullptr, (float*)nullptr);
 	}
 	count_launch();
 }
@@ -598,7 +628,7 @@ void launch_blend_backward(const b200gs_view_t& v, GeomState& gs, BinningState& 
 		const unsigned want = (units + BLEND_WARPS - 1) / BLEND_WARPS;
 		launch_blend(0u, blend_backward_kernel<true>, want < cap ? want : cap, smem, stream, (const uint2*)is.ranges,
 			(const uint32_t*)is.tile_order, (const uint32_t*)bs.sorted_vals, (const float4*)gs.rec,
-			v.width, v.height, gx, units, ticket, exits, v.background, (const float*)is.final_T, (const uint32_t*)is.n_contrib,
+			v.width, v.height, gx, units, ticket, exits, (const uint32_t*)bs.surv_bits, bs.surv_words, v.background, (const float*)is.final_T, (const uint32_t*)is.n_contrib,
 			gout.dL_dcolor, gout.dL_ddepth, gout.dL_dalpha, gout.dL_dfeature, grec);
 	} else {
 		static unsigned cap = 0;
@@ -607,7 +637,7 @@ void launch_blend_backward(const b200gs_view_t& v, GeomState& gs, BinningState& 
 		const unsigned want = (units + BLEND_WARPS - 1) / BLEND_WARPS;
 		launch_blend(0u, blend_backward_kernel<false>, want < cap ? want : cap, smem, stream, (const uint2*)is.ranges,
 			(const uint32_t*)is.tile_order, (const uint32_t*)bs.sorted_vals, (const float4*)gs.rec,
-			v.width, v.height, gx, units, ticket, exits, v.background, (const float*)is.final_T, (const uint32_t*)is.n_contrib,
+			v.width, v.height, gx, units, ticket, exits, (const uint32_t*)bs.surv_bits, bs.surv_words, v.background, (const float*)is.final_T, (const uint32_t*)is.n_contrib,
 			gout.dL_dcolor, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, grec);
 	}
 	count_launch();

@@ -69,6 +69,12 @@ struct BinningState {
 	uint32_t* lookback;  // [tiles_L][256]
 	uint32_t* sorted_vals;  // == point_list after the tile sort (val_a or val_b depending on pass parity)
 	uint32_t* sorted_keys;
+	// Survivor bitmap, [8 sub-blocks][surv_words]: bit (i & 31) of word (range.x >> 5) + tile + (i >> 5) of plane s says whether
+	// list entry i of the tile survived the conservative cull of 8x4 pixel block s.  Written by the blend forward (the ballot of
+	// every round it stages), read by the blend backward instead of fetching and culling the entry again.  The words of two
+	// tiles never collide: ranges are ordered by tile id and (x' >> 5) + t' >= (x >> 5) + floor(n / 32) + t + 1.
+	uint32_t* surv_bits;
+	size_t surv_words;
 	size_t bytes;
 };
 
@@ -117,7 +123,7 @@ void launch_debug_keys(const b200gs_view_t& v, GeomState& gs, BinningState& bs, 
                        cudaStream_t stream);
 
 void launch_blend_forward(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
-                          const b200gs_outputs_t& out, cudaStream_t stream, uint4* clean_words, size_t clean_count);
+                          const b200gs_outputs_t& out, cudaStream_t stream, uint4* clean_words, size_t clean_count);  // also writes bs.surv_bits
 void launch_finalize_header(GeomState& gs, int64_t capacity, cudaStream_t stream);
 void launch_blend_backward(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
                            const b200gs_grad_outputs_t& gout, float* grec, cudaStream_t stream);

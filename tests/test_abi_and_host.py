@@ -46,7 +46,7 @@ def test_workspace_sizes_are_monotone_and_aligned():
         assert b >= prev and b % 256 == 0
         prev = b
     assert lib.b200gs_geom_bytes(6_000_000) < 6_000_000 * 140  # ~ 116 B/Gaussian + look-back words
-    assert lib.b200gs_binning_bytes(10_000_000) < 10_000_000 * 18  # 16 B/instance (reference: > 24 B + CUB temp)
+    assert lib.b200gs_binning_bytes(10_000_000, 1920, 1080) < 10_000_000 * 19  # 16 B/instance + 1 bit per (instance, 8x4 block) + look-back words (reference: > 24 B + CUB temp)
     assert lib.b200gs_image_bytes(1920, 1080) >= 1920 * 1080 * 8
     assert lib.b200gs_scratch_bytes(1000) == 64000
 
