@@ -576,6 +576,8 @@ def run_b200gs(args, rank, world, local):
             except Exception as ex:  # never lose the headline line to an auxiliary measurement
                 extras[name] = dict(error=f"{type(ex).__name__}: {ex}")
             torch.cuda.empty_cache()
+        if rank == 0 and world == 1 and cpu is not None:
+            cpu["other_configs"] = cpu_baseline_other_configs()
 
     if rank == 0:
         line = dict(metric="rasterizer fwd+bwd views/s (1000/ms_per_step = ms/view; one view per train iteration)",
@@ -631,7 +633,30 @@ def train_b200gs(args, wl, capacity, rank, world, flush):
         n, ov = s.status()
         assert ov == 0, "binning capacity overflow in the training loop"
     ms_it = ms / args.steps
-    return dict(iters_per_s=world * 1000.0 / ms_it, ms_per_iter=ms_it, what=TRAIN_WHAT + ", whole iteration = one CUDA-graph replay"
+    densify = None
+    if world == 1:
+        # one densify_and_prune event on the trained state (clone / split / proximity / prune in the reference's row order, buffers
+        # re-allocated, the per-view graphs captured again): what the run pays every `densification_interval` = 100 iterations
+        accum, denom = tr.bucket.segment("xyz_gradient_accum"), tr.bucket.segment("denom")
+        thr = float(torch.quantile((accum / denom.clamp_min(1)).squeeze(), 0.95))
+        P0 = tr.P
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        tr.densify_and_prune(thr, 0.005, 4.4, None, iteration=1000, generator=torch.Generator(device=wl.dev).manual_seed(1))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tm = getattr(tr, "densify_timing", {})
+        densify = dict(ms_per_event=1000.0 * dt, P_before=P0, P_after=tr.P,
+                       breakdown_ms=dict(logic=1000.0 * tm.get("logic_s", 0.0), allocate=1000.0 * tm.get("allocate_s", 0.0),
+                                         recapture=1000.0 * tm.get("capture_s", 0.0)),
+                       amortised_ms_per_iteration=10.0 * dt,
+                       what="GaussianTrainer.densify_and_prune (scene/gaussian_model.py:513-608): top 5 % of the Gaussians by accumulated "
+                            "view-space gradient cloned or split, proximity (b200gs_knn3), prune; host-orchestrated torch row logic + re-capture of "
+                            "the per-view CUDA graphs; amortised over the reference's densification_interval of 100 iterations")
+        for i in range(3):  # and the trainer keeps going on the new Gaussian count
+            tr.step(i % nviews)
+        tr.loss_values()
+    return dict(iters_per_s=world * 1000.0 / ms_it, ms_per_iter=ms_it, densify=densify, what=TRAIN_WHAT + ", whole iteration = one CUDA-graph replay"
                 + ((" (gradient exchange inside the graph: reduce-scatter pushed by the backward kernel + gather kernel)" if tr.bucket.fused_exchange
                     else " + one all-reduce") if world > 1 else ""), last_loss=loss[0])
 
@@ -707,6 +732,32 @@ def cpu_baseline(wl, vi):
     sec = time.perf_counter() - t0
     return dict(value=1.0 / sec, unit="views/s", ms_per_view=1000.0 * sec, cores=orc.num_threads(), kind="port",
                 sample="1 view forward+backward of the same workload (oracle/gs_oracle.c, OpenMP)")
+
+
+def cpu_baseline_other_configs():
+    """The same CPU port on ONE view of the other BASELINE.json shapes (BASELINE.md section 3, B-cpu): configs[2] forward+backward,
+    configs[3] forward only (it is a render workload), configs[4] forward+backward.  ~30 s of host time in total."""
+    from oracle import cpu_oracle as orc
+    out = {}
+    for name, fwd_only in (("dtu_scan_3view", False), ("mip360_render", True), ("stress_train", False)):
+        try:
+            cfg = syn.CONFIGS[name]
+            sc = syn.make_config(name, views=1)
+            cam = sc.cameras[0]
+            t0 = time.perf_counter()
+            o = orc.forward(sc.means3D, sc.opacities, cam, np.zeros(3, np.float32), shs=sc.shs, scales=sc.scales, rotations=sc.rotations,
+                            extended=True, features=sc.features)
+            t1 = time.perf_counter()
+            if not fwd_only:
+                orc.backward(o, *syn.cotangents(cam, 100))
+            t2 = time.perf_counter()
+            out[name] = dict(P=cfg["P"], width=cfg["width"], height=cfg["height"], num_rendered=int(o["num_rendered"]),
+                             forward_ms=1000.0 * (t1 - t0), backward_ms=None if fwd_only else 1000.0 * (t2 - t1),
+                             ms_per_view=1000.0 * (t2 - t0), cores=orc.num_threads())
+            del o, sc
+        except Exception as ex:
+            out[name] = dict(error=f"{type(ex).__name__}: {ex}")
+    return out
 
 
 # ------------------------------------------------------------------------------------------ reference arm

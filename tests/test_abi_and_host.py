@@ -118,3 +118,37 @@ def test_product_never_touches_the_oracle():
                 txt = open(os.path.join(d, f)).read()
                 for n in needles:
                     assert n not in txt, f"{os.path.join(d, f)} references {n}"
+
+
+def test_reference_arm_of_the_bench_never_imports_the_product_library():
+    """bench.py --impl reference must not map libb200gs.so (the driver records the loaded .so files per arm): the functions of
+    that arm may import pure-Python helpers of the package (synthetic scenes, schedule, byte model) but nothing that loads _lib."""
+    import ast
+    src = open(os.path.join(helpers.ROOT, "bench.py")).read()
+    tree = ast.parse(src)
+    ref_funcs = {"run_reference", "train_reference", "RefBench", "cpu_baseline", "cpu_baseline_other_configs", "Workload", "train_targets",
+                 "raw_params", "event_loop", "wall_loop", "peaks", "ClockSampler", "parse", "dist_init", "main"}
+    loads_lib = ("b200gs._lib", "b200gs.rasterizer", "b200gs.trainer", "b200gs.parallel", "b200gs.hostio", "diff_gaussian_rasterization",
+                 "gaussian_renderer")
+    offenders = []
+    for node in tree.body:
+        if isinstance(node, (ast.FunctionDef, ast.ClassDef)) and node.name in ref_funcs:
+            if node.name == "Workload":
+                continue  # its settings() helper (our arm only) imports the drop-in package lazily
+            for sub in ast.walk(node):
+                mods = []
+                if isinstance(sub, ast.ImportFrom) and sub.module:
+                    mods = [sub.module] + [f"{sub.module}.{a.name}" for a in sub.names]
+                elif isinstance(sub, ast.Import):
+                    mods = [a.name for a in sub.names]
+                offenders += [(node.name, m) for m in mods if any(m == x or m.startswith(x + ".") for x in loads_lib)]
+        elif isinstance(node, (ast.Import, ast.ImportFrom)):  # module level: executed by both arms
+            mods = [node.module] + [f"{node.module}.{a.name}" for a in node.names] if isinstance(node, ast.ImportFrom) else [a.name for a in node.names]
+            offenders += [("<module>", m) for m in mods if m and any(m == x or m.startswith(x + ".") for x in loads_lib)]
+    assert not offenders, offenders
+    # and the pure-Python helpers really are pure: importing them maps no native library of ours
+    import subprocess, sys as _sys
+    code = ("import sys; sys.path.insert(0, %r); from b200gs import synthetic, schedule, bytes_model; "
+            "print('libb200gs' in open('/proc/self/maps').read())" % os.path.join(helpers.ROOT, "sdp-gs_b200"))
+    out = subprocess.run([_sys.executable, "-c", code], stdout=subprocess.PIPE, text=True, check=True).stdout.strip()
+    assert out == "False"
