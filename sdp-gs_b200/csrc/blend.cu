@@ -48,7 +48,8 @@ constexpr int BLEND_WARPS = B200GS_BLEND_WARPS;  // warps per CTA (each with a p
 constexpr int RING = 64;                         // survivor slots per warp
 constexpr int K_INFLIGHT = B200GS_K_INFLIGHT;    // commit groups (= rounds) of payload copies allowed in flight
 constexpr int BATCH = 16;                        // survivors per batch; ring positions of a batch never wrap
-constexpr int WSTRIDE = BATCH + 1;               // row stride of the pair-weight matrices (odd: conflict-free in both phases)
+constexpr int WSTRIDE = BATCH + 2;               // row stride of the pair-weight matrices: even, so phase 1 stores two weights at once; 18 l mod 32 is
+                                                 // conflict-free over a half-warp of 64-bit stores and over phase 2's 16 consecutive columns
 #define NOID 0xFFFFFFFFu
 
 __device__ __forceinline__ uint32_t sptr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -58,6 +59,20 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+#ifdef B200GS_BLEND_TRACE
+// developer builds only (tools/build_variants.sh ... "-DB200GS_BLEND_TRACE"): one record per blend unit, read back by tools/blend_trace.py
+__device__ uint32_t g_trace[2][1 << 16][8];
+__device__ __forceinline__ uint32_t trace_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (uint32_t)t; }
+__device__ __forceinline__ uint32_t trace_smid() { uint32_t v; asm("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
+__device__ __forceinline__ void trace_put(int dir, uint32_t unit, uint32_t t0, uint32_t c0, int n, int rounds, int surv) {
+	if ((threadIdx.x & 31) == 0 && unit < (1u << 16)) {
+		uint32_t* r = g_trace[dir][unit];
+		r[0] = unit; r[1] = trace_smid(); r[2] = t0; r[3] = trace_ns(); r[4] = (uint32_t)n; r[5] = (uint32_t)rounds; r[6] = (uint32_t)surv;
+		r[7] = (uint32_t)clock64() - c0;
+	}
+}
+#endif
 
 struct Unit {
 	uint32_t tile, sub;
@@ -87,15 +102,26 @@ __device__ __forceinline__ Unit make_unit(uint32_t unit, const uint32_t* order, 
 }
 
 // Per-warp shared memory.
+// Geometry of the staged survivors, two per entry so that one packed f32x2 instruction evaluates both:
+//   geo[j] = {x0, x1, y0, y1 | a0, a1, b0, b1 | c0, c1, o0, o1} for ring slots 2j (index 0) and 2j+1 (index 1).
+struct GeoPair {
+	float4 xy, ab, co;
+};
+__device__ __forceinline__ void geo_store(GeoPair* geo, int slot, const float4 g0, const float4 g1) {
+	float* p = reinterpret_cast<float*>(geo + (slot >> 1)) + (slot & 1);
+	p[0] = g0.x; p[2] = g0.y; p[4] = g0.z; p[6] = g0.w; p[8] = g1.x; p[10] = g1.y;
+}
 template <bool EXT>
 struct FwdSmem {
-	float4 g0[RING], g1[RING], g2[RING];
+	GeoPair geo[RING / 2];
+	float4 g2[RING];
 	float4 g3[EXT ? RING : 1];
 	uint32_t pos[RING];  // 1-based position of the survivor in its tile's list
 };
 template <bool EXT>
 struct BwdSmem {
-	float4 g0[RING], g1[RING], g2[RING];
+	float4 g0[RING], g1[RING];
+	float4 g2[RING];
 	float4 g3[EXT ? RING : 1];
 	uint32_t pos[RING];
 	uint32_t id[RING];
@@ -121,7 +147,7 @@ struct Walk {
 	}
 	// cull round r; survivors go to ring slots head.. in walk order, their payload copies are issued.  The round's survivor
 	// mask is left in `bits[r]` for the backward (BinningState::surv_bits).
-	template <bool EXT, bool WITH_ID, typename S>
+	template <bool EXT, typename S>
 	__device__ __forceinline__ int stage(S& s, int r, uint32_t id, const float4 g0, const float4 g1, const PixelBlock& pb, int head,
 	                                     uint32_t* bits) const {
 		const bool keep = id != NOID && !cull_block(g0, g1, pb);
@@ -133,16 +159,12 @@ struct Walk {
 			const float4* src = rec + 4 * (size_t)id + 2;
 			cp_async16(&s.g2[slot], src);
 			if (EXT) cp_async16(&s.g3[slot], src + 1);
-			s.g0[slot] = g0;
-			s.g1[slot] = g1;
+			geo_store(s.geo, slot, g0, g1);
 			s.pos[slot] = (uint32_t)(pos(32 * r + (int)lane) + 1);
-			if (WITH_ID) s.pos[RING + slot] = id;  // BwdSmem::id follows pos
 		}
 		return __popc(m);
 	}
 };
-static_assert(offsetof(BwdSmem<true>, id) == offsetof(BwdSmem<true>, pos) + RING * 4, "id follows pos");
-static_assert(offsetof(BwdSmem<false>, id) == offsetof(BwdSmem<false>, pos) + RING * 4, "id follows pos");
 
 // Persistent unit loop: lane 0 draws the next unit from the ticket; the last warp to run dry re-arms both
 // counters, so the kernel can be launched again on the same workspace without a memset.
@@ -173,7 +195,6 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_FWD_MIN_CTAS) blend_f
 	const float* __restrict__ bg, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
 	float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_alpha, float* __restrict__ out_feat)
 {
-	constexpr int NC = EXT ? 8 : 3;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	FwdSmem<EXT>& S = reinterpret_cast<FwdSmem<EXT>*>(smem_raw)[threadIdx.x >> 5];
 	const unsigned lane = threadIdx.x & 31;
@@ -194,6 +215,10 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_FWD_MIN_CTAS) blend_f
 
 	for (uint32_t unit = tk.next(lane); unit < units; unit = tk.next(lane)) {
 		const Unit u = make_unit(unit, order, ranges, W, H, grid_x);
+#ifdef B200GS_BLEND_TRACE
+		const uint32_t tr_t0 = trace_ns(), tr_c0 = (uint32_t)clock64();
+		int tr_rounds = 0, tr_surv = 0;
+#endif
 		Walk<true> wk;
 		wk.list = point_list + u.range.x; wk.rec = rec; wk.n = (int)(u.range.y - u.range.x); wk.top = 0; wk.lane = lane;
 		const int R = (wk.n + 31) >> 5;
@@ -203,9 +228,9 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_FWD_MIN_CTAS) blend_f
 		float T = 1.0f;
 		int lc = -1;                    // ring-absolute index of the last survivor blended into this pixel
 		uint32_t last_contributor = 0;  // ... and its 1-based list position (looked up once per batch)
-		float C[NC];
-#pragma unroll
-		for (int ch = 0; ch < NC; ch++) C[ch] = 0.f;
+		float2 C01 = make_float2(0.f, 0.f), C56 = C01;  // channel accumulators, (r,g) and (f0,f1) as packed pairs
+		float C2 = 0.f, C3 = 0.f, C4 = 0.f, C7 = 0.f;
+		const float2 npx = splat2(-u.pxf), npy = splat2(-u.pyf);
 
 		// Blend four staged survivors at ring slots base..base+3 (base % 4 == 0, front to back).  First the four alphas
 		// (independent), then the recurrence, branch-free: a pair that is skipped or comes after the pixel is saturated
@@ -213,18 +238,25 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_FWD_MIN_CTAS) blend_f
 		// pair (alpha = 0, test_T == T) can never trip the saturation test.
 		auto group4 = [&](int base, int abs0) {
 			float al[4];
+			bool pos_power[4];
 			float4 cc[4], ff[4];
 #pragma unroll
-			for (int k = 0; k < 4; k++) {
-				const float4 a = S.g0[base + k];
-				const float4 b = S.g1[base + k];
-				cc[k] = S.g2[base + k];
-				if (EXT) ff[k] = S.g3[base + k];
-				const float dx = __fsub_rn(a.x, u.pxf), dy = __fsub_rn(a.y, u.pyf);
-				const float power = pair_power(dx, dy, a.z, a.w, b.x);
-				const float alpha = fminf(0.99f, __fmul_rn(b.y, expf(power)));
-				al[k] = (power > 0.0f || alpha < 1.0f / 255.0f) ? 0.f : alpha;  // 0 <=> skipped pair (forward.cu:336-345)
+			for (int h = 0; h < 2; h++) {  // survivors (base + 2h, base + 2h + 1): one packed evaluation
+				const GeoPair& gp = S.geo[(base >> 1) + h];
+				const float4 xy = gp.xy, ab = gp.ab, co = gp.co;
+				cc[2 * h] = S.g2[base + 2 * h];
+				cc[2 * h + 1] = S.g2[base + 2 * h + 1];
+				if (EXT) { ff[2 * h] = S.g3[base + 2 * h]; ff[2 * h + 1] = S.g3[base + 2 * h + 1]; }
+				const float2 dx = add2(make_float2(xy.x, xy.y), npx), dy = add2(make_float2(xy.z, xy.w), npy);
+				const float2 power = pair_power2(dx, dy, make_float2(ab.x, ab.y), make_float2(ab.z, ab.w), make_float2(co.x, co.y));
+				const float2 oe = mul2(make_float2(co.z, co.w), expf2(power));
+				al[2 * h] = fminf(0.99f, oe.x);
+				al[2 * h + 1] = fminf(0.99f, oe.y);
+				pos_power[2 * h] = power.x > 0.0f;
+				pos_power[2 * h + 1] = power.y > 0.0f;
 			}
+#pragma unroll
+			for (int k = 0; k < 4; k++) al[k] = (pos_power[k] || al[k] < 1.0f / 255.0f) ? 0.f : al[k];  // 0 <=> skipped pair (forward.cu:336-345)
 			int lc_rel = -1;
 #pragma unroll
 			for (int k = 0; k < 4; k++) {
@@ -233,16 +265,14 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_FWD_MIN_CTAS) blend_f
 				const bool pdone = done || test_T < 0.0001f;
 				const float Tb = pdone ? 0.f : T;
 				// rgb: the reference's exact sequence fma(T, alpha*c, C) (forward.cu:355), images are bit-identical
-				C[0] = __fmaf_rn(Tb, __fmul_rn(alpha, cc[k].x), C[0]);
-				C[1] = __fmaf_rn(Tb, __fmul_rn(alpha, cc[k].y), C[1]);
-				C[2] = __fmaf_rn(Tb, __fmul_rn(alpha, cc[k].z), C[2]);
+				C01 = fma2(splat2(Tb), mul2(splat2(alpha), make_float2(cc[k].x, cc[k].y)), C01);
+				C2 = __fmaf_rn(Tb, __fmul_rn(alpha, cc[k].z), C2);
 				if (EXT) {
 					const float wt = __fmul_rn(alpha, Tb);
-					C[3] = __fmaf_rn(wt, cc[k].w, C[3]);
-					C[4] = __fadd_rn(C[4], wt);
-					C[5] = __fmaf_rn(wt, ff[k].x, C[5]);
-					C[6] = __fmaf_rn(wt, ff[k].y, C[6]);
-					C[7] = __fmaf_rn(wt, ff[k].z, C[7]);
+					C3 = __fmaf_rn(wt, cc[k].w, C3);
+					C4 = __fadd_rn(C4, wt);
+					C56 = fma2(splat2(wt), make_float2(ff[k].x, ff[k].y), C56);
+					C7 = __fmaf_rn(wt, ff[k].z, C7);
 				}
 				lc_rel = (!pdone && alpha != 0.f) ? k : lc_rel;
 				T = pdone ? T : test_T;
@@ -281,7 +311,10 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_FWD_MIN_CTAS) blend_f
 					all_done = __all_sync(0xFFFFFFFFu, done);
 					if (all_done) break;
 				}
-				head += wk.template stage<EXT, false>(S, r, ida, ga0, ga1, u.pb, head, bits);
+				head += wk.template stage<EXT>(S, r, ida, ga0, ga1, u.pb, head, bits);
+#ifdef B200GS_BLEND_TRACE
+				tr_rounds = r + 1; tr_surv = head;
+#endif
 				cp_commit();
 #pragma unroll
 				for (int j = K_INFLIGHT; j > 0; j--) hist[j] = hist[j - 1];
@@ -296,7 +329,8 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_FWD_MIN_CTAS) blend_f
 				if ((int)lane < pad) {
 					const int slot = (head + (int)lane) & (RING - 1);
 					const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-					S.g0[slot] = z; S.g1[slot] = z; S.g2[slot] = z;
+					geo_store(S.geo, slot, z, z);
+					S.g2[slot] = z;
 					if (EXT) S.g3[slot] = z;
 				}
 				head += pad;
@@ -310,27 +344,33 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_FWD_MIN_CTAS) blend_f
 			}
 			__syncwarp();  // the ring is reused by the next unit
 		}
+#ifdef B200GS_BLEND_TRACE
+		trace_put(0, unit, tr_t0, tr_c0, wk.n, tr_rounds, tr_surv);
+#endif
 		if (u.inside) {
 			const size_t pix = (size_t)u.py * W + u.px, HW = (size_t)H * W;
 			final_T[pix] = T;
 			n_contrib[pix] = last_contributor;
-			out_color[pix] = __fmaf_rn(bg0, T, C[0]);
-			out_color[HW + pix] = __fmaf_rn(bg1, T, C[1]);
-			out_color[2 * HW + pix] = __fmaf_rn(bg2, T, C[2]);
+			out_color[pix] = __fmaf_rn(bg0, T, C01.x);
+			out_color[HW + pix] = __fmaf_rn(bg1, T, C01.y);
+			out_color[2 * HW + pix] = __fmaf_rn(bg2, T, C2);
 			if (EXT) {
-				out_depth[pix] = C[3];
-				out_alpha[pix] = C[4];
-				out_feat[pix] = C[5];
-				out_feat[HW + pix] = C[6];
-				out_feat[2 * HW + pix] = C[7];
+				out_depth[pix] = C3;
+				out_alpha[pix] = C4;
+				out_feat[pix] = C56.x;
+				out_feat[HW + pix] = C56.y;
+				out_feat[2 * HW + pix] = C7;
 			}
 		}
 	}
 	tk.leave(lane, gridDim.x * BLEND_WARPS);
 }
 
+#ifndef B200GS_BWD_MIN_CTAS
+#define B200GS_BWD_MIN_CTAS 5  // shared memory allows 5 CTAs/SM; stating it lets ptxas use 96 registers instead of 72 (measured: -3 us)
+#endif
 template <bool EXT>
-__global__ void __launch_bounds__(BLEND_WARPS * 32) blend_backward_kernel(
+__global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_BWD_MIN_CTAS) blend_backward_kernel(
 	const uint2* ranges, const uint32_t* order, const uint32_t* point_list, const float4* rec,
 	int W, int H, int grid_x, uint32_t units, unsigned int* ticket, unsigned int* exits,
 	const uint32_t* surv_bits, size_t surv_words,
@@ -357,6 +397,9 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32) blend_backward_kernel(
 	for (uint32_t unit = tk.next(lane); unit < units; unit = tk.next(lane)) {
 		const Unit u = make_unit(unit, order, ranges, W, H, grid_x);
 		const size_t pix = (size_t)u.py * W + u.px, HW = (size_t)H * W;
+#ifdef B200GS_BLEND_TRACE
+		const uint32_t tr_t0 = trace_ns(), tr_c0 = (uint32_t)clock64();
+#endif
 
 		// everything the unit needs from the image planes is requested at once, ahead of the wmax == 0 test
 		const float T_final = u.inside ? __ldcg(final_T + pix) : 0.f;
@@ -383,6 +426,7 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32) blend_backward_kernel(
 		S.basis[lane][1][1] = EXT ? make_float4(dpix[5], dpix[6], dpix[7], 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
 		const float bg_dot_dpixel = bg0 * dpix[0] + bg1 * dpix[1] + bg2 * dpix[2];
 		float A = 0.f, lastD = 0.f, last_alpha = 0.f;
+		const float2 d01 = make_float2(dpix[0], dpix[1]), d23 = make_float2(dpix[2], EXT ? dpix[3] : 0.f), d56 = make_float2(EXT ? dpix[5] : 0.f, EXT ? dpix[6] : 0.f);
 
 		Walk<false> wk;
 		wk.list = point_list + u.range.x; wk.rec = rec; wk.n = (int)wmax; wk.top = (int)wmax - 1; wk.lane = lane;
@@ -395,19 +439,22 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32) blend_backward_kernel(
 			// carried as one scalar, A = sum_ch accum_rec[ch] * dL/dpixel[ch].
 			float* wrow = &S.w[0][lane * WSTRIDE];
 			for (int k0 = 0; k0 < cpad; k0 += 2) {
-				float Gk[2], al[2], op[2];
-				bool act[2];
+				float Gk[2], op[2], pw[2], al[2];
 #pragma unroll
 				for (int k = 0; k < 2; k++) {
 					const float4 a = S.g0[base + k0 + k];
 					const float4 b = S.g1[base + k0 + k];
 					const float dx = __fsub_rn(a.x, u.pxf), dy = __fsub_rn(a.y, u.pyf);
-					const float power = pair_power(dx, dy, a.z, a.w, b.x);
+					pw[k] = pair_power(dx, dy, a.z, a.w, b.x);
 					op[k] = b.y;
-					Gk[k] = exp_fast(power);
+					Gk[k] = exp_fast(pw[k]);
 					al[k] = fminf(0.99f, __fmul_rn(b.y, Gk[k]));
-					act[k] = (S.pos[base + k0 + k] <= last_contributor) && !(power > 0.0f) && !(al[k] < 1.0f / 255.0f);
 				}
+				bool act[2];
+				float wgs[2], wcs[2];
+#pragma unroll
+				for (int k = 0; k < 2; k++)
+					act[k] = (S.pos[base + k0 + k] <= last_contributor) && !(pw[k] > 0.0f) && !(al[k] < 1.0f / 255.0f);
 #pragma unroll
 				for (int k = 0; k < 2; k++) {
 					float wg = 0.f, wc = 0.f;
@@ -416,10 +463,15 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32) blend_backward_kernel(
 						const float inv = rcp_approx(1.0f - alpha);
 						T *= inv;
 						const float4 c = S.g2[base + k0 + k];
-						float D = c.x * dpix[0] + c.y * dpix[1] + c.z * dpix[2];
+						float D;
 						if (EXT) {
 							const float4 f = S.g3[base + k0 + k];
-							D += c.w * dpix[3] + dpix[4] + f.x * dpix[5] + f.y * dpix[6] + f.z * dpix[7];
+							float2 Dp = mul2(make_float2(c.x, c.y), d01);
+							Dp = fma2(make_float2(c.z, c.w), d23, Dp);
+							Dp = fma2(make_float2(f.x, f.y), d56, Dp);
+							D = (Dp.x + Dp.y) + fmaf(f.z, dpix[7], dpix[4]);
+						} else {
+							D = c.x * dpix[0] + c.y * dpix[1] + c.z * dpix[2];
 						}
 						A = last_alpha * lastD + (1.f - last_alpha) * A;
 						lastD = D;
@@ -428,28 +480,30 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32) blend_backward_kernel(
 						wg = Gk[k] * (op[k] * dL_dalpha);  // G * dL/dG; clamp ignored as in backward.cu:538
 						wc = alpha * T;
 					}
-					wrow[k0 + k] = wg;
-					wrow[32 * WSTRIDE + 16 + k0 + k] = wc;  // S.w[1]
+					wgs[k] = wg; wcs[k] = wc;
 				}
+				*reinterpret_cast<float2*>(wrow + k0) = make_float2(wgs[0], wgs[1]);
+				*reinterpret_cast<float2*>(wrow + 32 * WSTRIDE + 16 + k0) = make_float2(wcs[0], wcs[1]);  // S.w[1]
 			}
 			__syncwarp();
 			// ---- phase 2: lane = (half h, Gaussian g).  h = 0: pixel moments of wg; h = 1: channel sums of wc.
 			const int g = (int)(lane & 15u), h = (int)(lane >> 4);
 			if (g < count) {
-				float acc[NACC];
-#pragma unroll
-				for (int k = 0; k < NACC; k++) acc[k] = 0.f;
+				// packed sums: (acc0, acc1), (acc2, acc3), (acc4, acc5) advance with one FFMA2 each
+				float2 a01 = make_float2(0.f, 0.f), a23 = a01, a45 = a01;
+				float a6 = 0.f;
 				const float* wcol = S.w[h] + g;
 #pragma unroll
 				for (int p = 0; p < 32; p++) {
-					const float wv = wcol[p * WSTRIDE];
+					const float2 wv = splat2(wcol[p * WSTRIDE]);
 					const float4 b0 = S.basis[p][h][0];
-					acc[0] = fmaf(wv, b0.x, acc[0]); acc[1] = fmaf(wv, b0.y, acc[1]); acc[2] = fmaf(wv, b0.z, acc[2]);
-					acc[3] = fmaf(wv, b0.w, acc[3]);
+					a01 = fma2(wv, make_float2(b0.x, b0.y), a01);
+					a23 = fma2(wv, make_float2(b0.z, b0.w), a23);
 					const float4 b1 = S.basis[p][h][1];
-					acc[4] = fmaf(wv, b1.x, acc[4]); acc[5] = fmaf(wv, b1.y, acc[5]);
-					if (EXT) acc[6] = fmaf(wv, b1.z, acc[6]);
+					a45 = fma2(wv, make_float2(b1.x, b1.y), a45);
+					if (EXT) a6 = fmaf(wv.x, b1.z, a6);
 				}
+				const float acc[7] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y, a6};
 				bool any = false;
 #pragma unroll
 				for (int k = 0; k < NACC; k++) any = any || (acc[k] != 0.f);
@@ -541,6 +595,9 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32) blend_backward_kernel(
 				tail += c;
 			}
 		}
+#ifdef B200GS_BLEND_TRACE
+		trace_put(1, unit, tr_t0, tr_c0, wk.n, R, head);
+#endif
 	}
 	tk.leave(lane, gridDim.x * BLEND_WARPS);
 }
@@ -589,6 +646,12 @@ cudaError_t launch_blend(unsigned site, void (*kernel)(KArgs...), unsigned grid,
 }
 
 }  // namespace
+
+#ifdef B200GS_BLEND_TRACE
+extern "C" int b200gs_debug_blend_trace(uint32_t* host_out, int dir) {
+	return (int)cudaMemcpyFromSymbol(host_out, g_trace, sizeof(uint32_t) * (1 << 16) * 8, (size_t)dir * sizeof(uint32_t) * (1 << 16) * 8);
+}
+#endif
 
 void launch_blend_forward(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
                           const b200gs_outputs_t& out, cudaStream_t stream, uint4* clean_words, size_t clean_count) {

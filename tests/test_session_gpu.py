@@ -82,7 +82,8 @@ def test_accumulate_sums_views_inside_the_backward_kernel():
         want = solo[0].grads[k] + solo[1].grads[k]
         assert rel_err(shared[k].cpu().numpy(), want.cpu().numpy()) <= 1e-6, k
     # means2D (the densification input) is per view: never accumulated
-    torch.testing.assert_close(acc[1].grads["means2D"], solo[1].grads["means2D"], rtol=1e-5, atol=1e-7)  # (float REDs: run-to-run last bits)
+    # (float REDs in a different order on every run: elementwise last bits differ, so the check is on the tensor's scale)
+    assert rel_err(acc[1].grads["means2D"].cpu().numpy(), solo[1].grads["means2D"].cpu().numpy()) <= 1e-6
 
 
 @gpu
