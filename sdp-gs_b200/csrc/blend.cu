@@ -63,6 +63,7 @@ __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0
 #ifdef B200GS_BLEND_TRACE
 // developer builds only (tools/build_variants.sh ... "-DB200GS_BLEND_TRACE"): one record per blend unit, read back by tools/blend_trace.py
 __device__ uint32_t g_trace[2][1 << 16][8];
+__device__ uint32_t g_unit_lo = 0;  // B200GS_BLEND_UNIT_RANGE=lo,hi: only these units are processed (profiling a slice of the schedule)
 __device__ __forceinline__ uint32_t trace_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (uint32_t)t; }
 __device__ __forceinline__ uint32_t trace_smid() { uint32_t v; asm("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
 __device__ __forceinline__ void trace_put(int dir, uint32_t unit, uint32_t t0, uint32_t c0, int n, int rounds, int surv) {
@@ -213,7 +214,12 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_FWD_MIN_CTAS) blend_f
 		hdr->sort_barrier[0] = 0u; hdr->sort_barrier[1] = 0u;
 	}
 
-	for (uint32_t unit = tk.next(lane); unit < units; unit = tk.next(lane)) {
+#ifdef B200GS_BLEND_TRACE
+#define TK_NEXT (tk.next(lane) + g_unit_lo)
+#else
+#define TK_NEXT tk.next(lane)
+#endif
+	for (uint32_t unit = TK_NEXT; unit < units; unit = TK_NEXT) {
 		const Unit u = make_unit(unit, order, ranges, W, H, grid_x);
 #ifdef B200GS_BLEND_TRACE
 		const uint32_t tr_t0 = trace_ns(), tr_c0 = (uint32_t)clock64();
@@ -533,13 +539,19 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_BWD_MIN_CTAS) blend_b
 		// fetched nor culled again here: lanes read their bit and their id two rounds ahead, and survivors have their whole
 		// 64-byte record copied into the ring by cp.async.
 		const uint32_t* bits = surv_bits + (size_t)u.sub * surv_words + (u.range.x >> 5) + u.tile;
-		auto load_entry = [&](int r, uint32_t& id) {  // id of walk entry 32 r + lane, NOID when it did not survive (or is past the end)
+		// Register pipeline, as in the forward: the survivor word of round r+3 and the id of round r+2 (fetched only when its bit
+		// is set in the word requested a round earlier) are requested at the end of round r, after the rotation.
+		auto load_word = [&](int r) -> uint32_t {  // survivor-bitmap word that holds the bit of walk entry 32 r + lane
 			const int i = 32 * r + (int)lane;
-			id = NOID;
+			return i < wk.n ? __ldcg(bits + ((wk.top - i) >> 5)) : 0u;
+		};
+		auto load_entry = [&](int r, uint32_t word) -> uint32_t {  // id of walk entry 32 r + lane, NOID when it did not survive (or is past the end)
+			const int i = 32 * r + (int)lane;
 			if (i < wk.n) {
 				const int p = wk.top - i;
-				if ((__ldcg(bits + (p >> 5)) >> (p & 31)) & 1u) id = __ldcg(wk.list + p);
+				if ((word >> (p & 31)) & 1u) return __ldcg(wk.list + p);
 			}
+			return NOID;
 		};
 		auto stage = [&](int r, uint32_t id, int hd) -> int {
 			const unsigned m = __ballot_sync(0xFFFFFFFFu, id != NOID);
@@ -556,17 +568,14 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_BWD_MIN_CTAS) blend_b
 			}
 			return __popc(m);
 		};
-		uint32_t ida, idb;
-		load_entry(0, ida);
-		load_entry(1, idb);
+		uint32_t ida = load_entry(0, load_word(0)), idb = load_entry(1, load_word(1)), idc = load_entry(2, load_word(2));
+		uint32_t wd = load_word(3);
 		int head = 0, tail = 0;
 		int hist[K_INFLIGHT + 1];
 #pragma unroll
 		for (int j = 0; j <= K_INFLIGHT; j++) hist[j] = 0;
 		__syncwarp();  // basis visible
 		for (int r = 0; r < R; r++) {
-			uint32_t idc;
-			load_entry(r + 2, idc);
 			cp_wait<K_INFLIGHT>();
 			if (hist[K_INFLIGHT] - tail >= BATCH || head - tail > RING - 32) {
 				if (head - tail > RING - 32) { cp_wait<0>(); hist[K_INFLIGHT] = head; }
@@ -579,6 +588,8 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_BWD_MIN_CTAS) blend_b
 			for (int j = K_INFLIGHT; j > 0; j--) hist[j] = hist[j - 1];
 			hist[0] = head;
 			ida = idb; idb = idc;
+			idc = load_entry(r + 3, wd);
+			wd = load_word(r + 4);
 		}
 		cp_wait<0>();
 		if (head > tail) {
@@ -656,7 +667,13 @@ extern "C" int b200gs_debug_blend_trace(uint32_t* host_out, int dir) {
 void launch_blend_forward(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
                           const b200gs_outputs_t& out, cudaStream_t stream, uint4* clean_words, size_t clean_count) {
 	const int gx = (v.width + TILE_X - 1) / TILE_X, gy = (v.height + TILE_Y - 1) / TILE_Y;
-	const unsigned units = (unsigned)(gx * gy * 8);
+	unsigned units = (unsigned)(gx * gy * 8);
+#ifdef B200GS_BLEND_TRACE
+	if (const char* e = getenv("B200GS_BLEND_UNIT_RANGE")) {
+		unsigned lo = 0, hi = units;
+		if (sscanf(e, "%u,%u", &lo, &hi) == 2) { cudaMemcpyToSymbol(g_unit_lo, &lo, 4); if (hi < units) units = hi; }
+	}
+#endif
 	if (v.extended) {
 		static unsigned cap = 0;
 		constexpr size_t smem = BLEND_WARPS * sizeof(FwdSmem<true>);
