@@ -129,6 +129,8 @@ ImageState image_from_chunk(char* base, int W, int H) {
 	carve(p, s.final_T, N ? N : 1);
 	carve(p, s.n_contrib, N ? N : 1);
 	carve(p, s.tile_count, (tiles ? tiles : 1) * (size_t)tile_count_stride());
+	carve(p, s.tile_cost, 2 * (tiles ? tiles : 1));
+	carve(p, s.tile_order_bwd, tiles ? tiles : 1);
 	s.bytes = align_up((size_t)(p - base), 256) + 256;
 	return s;
 }
@@ -246,6 +248,7 @@ int b200gs_workspace_init(const b200gs_workspace_t* ws, int32_t P, void* scratch
 	cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
 	cudaError_t e = cudaMemsetAsync(ws->geom, 0, geom_zero_len(P), stream);
 	if (e == cudaSuccess && scratch) e = cudaMemsetAsync(scratch, 0, b200gs_scratch_bytes(P), stream);
+	if (e == cudaSuccess && ws->image && ws->image_bytes) e = cudaMemsetAsync(ws->image, 0, ws->image_bytes, stream);  // no cost history yet
 	if (e != cudaSuccess) return fail(B200GS_E_CUDA, "[CUDA ERROR] workspace_init: %s", cudaGetErrorString(e));
 	return 0;
 }
@@ -297,7 +300,7 @@ static int forward_render_impl(const b200gs_view_t* v, const b200gs_gaussians_t*
 	resolve_sorted(v, bs);
 	const size_t tiles = (size_t)((v->width + TILE_X - 1) / TILE_X) * ((v->height + TILE_Y - 1) / TILE_Y);
 	if (P > 0 && capacity > 0) {
-		{ StageScope t(stream, ST_EMIT); launch_scan_emit(*v, gs, bs, is, P, capacity, stream, chained); }
+		{ StageScope t(stream, ST_EMIT); launch_scan_emit(*v, gs, bs, is, P, capacity, stream, chained, ws->persistent != 0); }
 		if (int e = check_stage(v, stream, "instance offsets / duplicate-with-keys")) return e;
 		{ StageScope t(stream, ST_TILE_SORT); launch_tile_sort(*v, gs, bs, capacity, stream); }
 		if (int e = check_stage(v, stream, "tile sort")) return e;
@@ -305,14 +308,14 @@ static int forward_render_impl(const b200gs_view_t* v, const b200gs_gaussians_t*
 	const bool emitted = P > 0 && capacity > 0;
 	if (P > 0 && !emitted) launch_finalize_header(gs, capacity, stream);  // the status words scan_emit assigns
 	if (!emitted || !tile_counts_path((int)tiles)) {  // small tile grids: scan_emit's last CTA already built ranges + schedule
-		{ StageScope t(stream, ST_RANGES); launch_tile_ranges(*v, gs, bs, is, emitted ? capacity : 0, stream); }
+		{ StageScope t(stream, ST_RANGES); launch_tile_ranges(*v, gs, bs, is, emitted ? capacity : 0, stream, ws->persistent != 0); }
 		if (int e = check_stage(v, stream, "tile ranges / schedule")) return e;
 	}
 	{
 		StageScope t(stream, ST_BLEND_FWD);
 		char* gbase = reinterpret_cast<char*>(ws->geom);
 		launch_blend_forward(*v, gs, bs, is, *out, stream, reinterpret_cast<uint4*>(gbase + sizeof(GeomHeader)),
-		                     (geom_zero_len(P) - sizeof(GeomHeader)) / sizeof(uint4));
+		                     (geom_zero_len(P) - sizeof(GeomHeader)) / sizeof(uint4), ws->persistent != 0);
 	}
 	return check_stage(v, stream, "blend forward");
 }
@@ -365,7 +368,7 @@ int b200gs_backward(const b200gs_view_t* v, const b200gs_gaussians_t* g, const i
 	resolve_sorted(v, bs);
 	float* grec = reinterpret_cast<float*>(grads->scratch);
 	if (!ws->persistent) { StageScope t(stream, ST_MEMSET); cudaMemsetAsync(grec, 0, b200gs_scratch_bytes(P), stream); }
-	{ StageScope t(stream, ST_BLEND_BWD); launch_blend_backward(*v, gs, bs, is, *gout, grec, stream); }
+	{ StageScope t(stream, ST_BLEND_BWD); launch_blend_backward(*v, gs, bs, is, *gout, grec, stream, ws->persistent != 0); }
 	if (int e = check_stage(v, stream, "blend backward")) return e;
 	{ StageScope t(stream, ST_PREPROCESS_BWD); launch_preprocess_backward(*v, *g, radii, gs, grec, *grads, ws->persistent != 0, stream); }
 	return check_stage(v, stream, "preprocess backward");

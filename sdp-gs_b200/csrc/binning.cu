@@ -282,13 +282,58 @@ constexpr int EMIT_ITEMS = SCAN_ITEMS;
 constexpr int COUNT_TILES_MAX = 2048;
 constexpr int COUNT_STRIDE = 32;  // words between two tiles' global counters
 
+// Launch orders of the blend units (forward, backward): tile ids, heaviest first.  Weight of a tile = what its units cost the
+// last time this workspace rendered (ImageState::tile_cost, persistent workspaces) or, without history, the length of its
+// list.  Counting sort on a 7-bit key (position of the leading one + the next two bits), descending; the order inside a
+// bucket is arbitrary (blend units are independent of each other).  Called by every thread of one CTA; s_cnt is zero on entry.
+// The cost words are consumed: left zero for the blend kernels of this call to accumulate into.
+__device__ __forceinline__ uint32_t order_key(uint32_t w) {
+	if (w == 0) return 0u;
+	const int msb = 31 - __clz(w);
+	const uint32_t frac = msb >= 2 ? (w >> (msb - 2)) & 3u : (w << (2 - msb)) & 3u;
+	return min(127u, (uint32_t)(msb + 1) * 4u + frac - 3u);
+}
+template <typename LenFn>
+__device__ __forceinline__ void build_blend_orders(int tid, int nthreads, int tiles, LenFn len_of, uint32_t* cost, uint32_t* order_fwd,
+                                                   uint32_t* order_bwd, uint32_t (*s_cnt)[128], uint32_t (*s_off)[128]) {
+	for (int t = tid; t < tiles; t += nthreads) {
+		uint32_t kf = order_key(len_of(t)), kb = kf;
+		if (cost) {
+			const uint32_t cf = __ldcg(cost + t), cb = __ldcg(cost + tiles + t);
+			if (cf) kf = order_key(cf);
+			if (cb) kb = order_key(cb);
+			cost[t] = kf | (kb << 8);  // kept for the second pass (same thread)
+		}
+		atomicAdd(&s_cnt[0][kf], 1u);
+		atomicAdd(&s_cnt[1][kb], 1u);
+	}
+	__syncthreads();
+	if (tid < 2) {
+		uint32_t run = 0;
+		for (int k = 127; k >= 0; k--) { s_off[tid][k] = run; run += s_cnt[tid][k]; }
+	}
+	__syncthreads();
+	for (int t = tid; t < tiles; t += nthreads) {
+		uint32_t kf, kb;
+		if (cost) {
+			const uint32_t pk = cost[t];
+			kf = pk & 255u; kb = pk >> 8;
+			cost[t] = 0u; cost[tiles + t] = 0u;
+		} else {
+			kf = kb = order_key(len_of(t));
+		}
+		order_fwd[atomicAdd(&s_off[0][kf], 1u)] = (uint32_t)t;
+		order_bwd[atomicAdd(&s_off[1][kb], 1u)] = (uint32_t)t;
+	}
+}
+
 template <bool TILE_COUNTS>
 __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(
 	const uint32_t* __restrict__ order, const ushort4* __restrict__ rect, int P, uint32_t grid_x, int64_t capacity,
 	int tile_bits, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ scan_state,
 	uint32_t* __restrict__ tile_hist /*[4][256]*/, uint32_t* __restrict__ zero_words, size_t zero_count,
 	GeomHeader* __restrict__ hdr, uint32_t* __restrict__ tile_count, int tiles, uint2* __restrict__ ranges,
-	uint32_t* __restrict__ tile_order)
+	uint32_t* __restrict__ tile_order, uint32_t* __restrict__ tile_order_bwd, uint32_t* tile_cost /* nullptr: no history */)
 {
 	constexpr int TILE = EMIT_THREADS * EMIT_ITEMS;
 	__shared__ uint32_t s_warp[EMIT_THREADS / 32];
@@ -296,12 +341,12 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(
 	__shared__ uint32_t s_tile;
 	__shared__ bool s_last;
 	__shared__ uint32_t s_ph[4][256];  // digit histograms of the tile-sort passes (TILE_COUNTS: built by the last CTA from the tile counts)
-	__shared__ uint32_t s_cnt[128], s_off[128];
+	__shared__ uint32_t s_cnt[2][128], s_off[2][128];
 	__shared__ uint32_t s_tc[TILE_COUNTS ? COUNT_TILES_MAX : 1];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	pdl_trigger();
 	for (int i = tid; i < 4 * 256; i += EMIT_THREADS) (&s_ph[0][0])[i] = 0;
-	if (tid < 128) s_cnt[tid] = 0;
+	if (tid < 256) (&s_cnt[0][0])[tid] = 0;
 	if (TILE_COUNTS) for (int i = tid; i < tiles; i += EMIT_THREADS) s_tc[i] = 0;
 	pdl_wait();
 	if (tid == 0) s_tile = atomicAdd(&hdr->scan_ticket, 1u);
@@ -414,12 +459,6 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(
 	__syncthreads();
 	if (!s_last) return;
 	__threadfence();
-	auto key_of = [](uint32_t len) -> uint32_t {
-		if (len == 0) return 0u;
-		const int msb = 31 - __clz(len);
-		const uint32_t frac = msb >= 2 ? (len >> (msb - 2)) & 3u : (len << (2 - msb)) & 3u;
-		return min(127u, (uint32_t)(msb + 1) * 4u + frac - 3u);
-	};
 	const int passes = (tile_bits + 7) / 8;
 	uint32_t running = 0;
 	for (int t0 = 0; t0 < tiles; t0 += EMIT_THREADS) {
@@ -445,18 +484,13 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(
 			if (c) {
 				for (int p = 0; p < passes; p++) atomicAdd(&s_ph[p][((uint32_t)t >> (8 * p)) & 255u], c);
 			}
-			atomicAdd(&s_cnt[key_of(c)], 1u);
 		}
 		running += tot;
 	}
 	__syncthreads();
 	for (int i = tid; i < passes * 256; i += EMIT_THREADS) tile_hist[i] = (&s_ph[0][0])[i];
-	if (tid == 0) {
-		uint32_t run = 0;
-		for (int k = 127; k >= 0; k--) { s_off[k] = run; run += s_cnt[k]; }
-	}
-	__syncthreads();
-	for (int t = tid; t < tiles; t += EMIT_THREADS) tile_order[atomicAdd(&s_off[key_of(__ldcg(tile_count + (size_t)t * COUNT_STRIDE))], 1u)] = (uint32_t)t;
+	build_blend_orders(tid, EMIT_THREADS, tiles, [&](int t) { return __ldcg(tile_count + (size_t)t * COUNT_STRIDE); }, tile_cost, tile_order,
+	                   tile_order_bwd, s_cnt, s_off);
 }
 
 // K5: identifyTileRanges (rasterizer_impl.cu:116-138; `ranges` zero-initialised by the preprocess kernel, :310),
@@ -465,7 +499,8 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(
 // by descending key; order inside a bucket is arbitrary (blend units are independent of each other).
 __global__ void __launch_bounds__(256) tile_ranges_schedule_kernel(
 	const uint32_t* __restrict__ tile_keys, int64_t n_max, const unsigned long long* __restrict__ n_dev,
-	uint2* __restrict__ ranges, int tiles, uint32_t* __restrict__ order, unsigned int* __restrict__ done_counter)
+	uint2* __restrict__ ranges, int tiles, uint32_t* __restrict__ order, uint32_t* __restrict__ order_bwd, uint32_t* tile_cost /* nullptr: no history */,
+	unsigned int* __restrict__ done_counter)
 {
 	pdl_trigger();
 	pdl_wait();
@@ -497,33 +532,19 @@ __global__ void __launch_bounds__(256) tile_ranges_schedule_kernel(
 		}
 	}
 	__shared__ bool s_last;
-	__shared__ uint32_t s_cnt[128];
-	__shared__ uint32_t s_off[128];
+	__shared__ uint32_t s_cnt[2][128], s_off[2][128];
 	__syncthreads();
 	const int tid = threadIdx.x;
 	if (tid == 0) {
 		__threadfence();  // cumulative: orders the whole CTA's range writes (observed through the barrier) before the ticket
 		s_last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
 	}
-	if (tid < 128) s_cnt[tid] = 0;
+	(&s_cnt[0][0])[tid] = 0;  // 256 threads
 	__syncthreads();
 	if (!s_last) return;
 	__threadfence();
-	auto key_of = [](uint2 r) -> uint32_t {
-		const uint32_t len = r.y - r.x;
-		if (len == 0) return 0u;
-		const int msb = 31 - __clz(len);
-		const uint32_t frac = msb >= 2 ? (len >> (msb - 2)) & 3u : (len << (2 - msb)) & 3u;
-		return min(127u, (uint32_t)(msb + 1) * 4u + frac - 3u);
-	};
-	for (int t = tid; t < tiles; t += blockDim.x) atomicAdd(&s_cnt[key_of(__ldcg(ranges + t))], 1u);
-	__syncthreads();
-	if (tid == 0) {
-		uint32_t run = 0;
-		for (int k = 127; k >= 0; k--) { s_off[k] = run; run += s_cnt[k]; }
-	}
-	__syncthreads();
-	for (int t = tid; t < tiles; t += blockDim.x) order[atomicAdd(&s_off[key_of(__ldcg(ranges + t))], 1u)] = (uint32_t)t;
+	build_blend_orders(tid, (int)blockDim.x, tiles, [&](int t) { const uint2 r = __ldcg(ranges + t); return r.y - r.x; }, tile_cost, order, order_bwd,
+	                   s_cnt, s_off);
 }
 
 __global__ void __launch_bounds__(256) debug_keys_kernel(const uint32_t* __restrict__ tile_keys, const uint32_t* __restrict__ point_list,
@@ -611,7 +632,7 @@ void launch_depth_order(GeomState& gs, int P, cudaStream_t stream) {
 	launch_radix_sort(gs.key_a, gs.key_b, gs.order, gs.val_b, P, nullptr, 32, gs.hist, gs.lookback, tickets, &gs.hdr->sort_barrier[0], stream);
 }
 
-void launch_scan_emit(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is, int P, int64_t capacity, cudaStream_t stream, bool chained) {
+void launch_scan_emit(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is, int P, int64_t capacity, cudaStream_t stream, bool chained, bool history) {
 	if (P <= 0) return;
 	const uint32_t gx = (v.width + TILE_X - 1) / TILE_X, gy = (v.height + TILE_Y - 1) / TILE_Y;
 	const int bit = (int)higher_msb(gx * gy);
@@ -622,11 +643,11 @@ void launch_scan_emit(const b200gs_view_t& v, GeomState& gs, BinningState& bs, I
 	if (tile_counts_path(tiles))
 		launch_impl(chained ? PDL_EMIT : 0u, scan_emit_kernel<true>, dim3(grid), dim3(EMIT_THREADS), stream, (const uint32_t*)gs.order, (const ushort4*)gs.rect, P, gx, capacity, bit,
 			bs.key_a, bs.val_a, reinterpret_cast<uint32_t*>(gs.scan_state), gs.hist + 4 * 256, bs.lookback, (size_t)passes * tiles_L * 256, gs.hdr,
-			is.tile_count, tiles, is.ranges, is.tile_order);
+			is.tile_count, tiles, is.ranges, is.tile_order, is.tile_order_bwd, history ? is.tile_cost : (uint32_t*)nullptr);
 	else
 		launch_impl(chained ? PDL_EMIT : 0u, scan_emit_kernel<false>, dim3(grid), dim3(EMIT_THREADS), stream, (const uint32_t*)gs.order, (const ushort4*)gs.rect, P, gx, capacity, bit,
 			bs.key_a, bs.val_a, reinterpret_cast<uint32_t*>(gs.scan_state), gs.hist + 4 * 256, bs.lookback, (size_t)passes * tiles_L * 256, gs.hdr,
-			is.tile_count, tiles, is.ranges, is.tile_order);
+			is.tile_count, tiles, is.ranges, is.tile_order, is.tile_order_bwd, history ? is.tile_cost : (uint32_t*)nullptr);
 	count_launch();
 }
 
@@ -641,7 +662,7 @@ void launch_tile_sort(const b200gs_view_t& v, GeomState& gs, BinningState& bs, i
 	bs.sorted_vals = where ? bs.val_b : bs.val_a;
 }
 
-void launch_tile_ranges(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is, int64_t capacity, cudaStream_t stream) {
+void launch_tile_ranges(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is, int64_t capacity, cudaStream_t stream, bool history) {
 	const unsigned long long* n_dev = &gs.hdr->num_rendered;
 	const int tiles = ((v.width + TILE_X - 1) / TILE_X) * ((v.height + TILE_Y - 1) / TILE_Y);
 	const int64_t n_max = capacity > 0 ? capacity : 0;
@@ -649,7 +670,8 @@ void launch_tile_ranges(const b200gs_view_t& v, GeomState& gs, BinningState& bs,
 	const int64_t chunks = (n_max + 1023) / 1024;  // 256 threads x 4 keys
 	const unsigned grid = (unsigned)(n_max > 0 ? (chunks < 148 * 8 ? chunks : 148 * 8) : 1);
 	unsigned int* counter = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(gs.hdr) + offsetof(GeomHeader, ranges_done));
-	launch_k(PDL_RANGES, tile_ranges_schedule_kernel, dim3(grid), dim3(256), stream, (const uint32_t*)bs.sorted_keys, n_max, n_dev, is.ranges, tiles, is.tile_order, counter);
+	launch_k(PDL_RANGES, tile_ranges_schedule_kernel, dim3(grid), dim3(256), stream, (const uint32_t*)bs.sorted_keys, n_max, n_dev, is.ranges, tiles, is.tile_order, is.tile_order_bwd,
+	         history ? is.tile_cost : (uint32_t*)nullptr, counter);
 	count_launch();
 }
 

@@ -26,6 +26,7 @@
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 #include "common.cuh"
 #include "blend_common.cuh"
 
@@ -63,6 +64,7 @@ __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0
 #ifdef B200GS_BLEND_TRACE
 // developer builds only (tools/build_variants.sh ... "-DB200GS_BLEND_TRACE"): one record per blend unit, read back by tools/blend_trace.py
 __device__ uint32_t g_trace[2][1 << 16][8];
+__device__ uint32_t g_trace2[1 << 16][4];
 __device__ uint32_t g_unit_lo = 0;  // B200GS_BLEND_UNIT_RANGE=lo,hi: only these units are processed (profiling a slice of the schedule)
 __device__ __forceinline__ uint32_t trace_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (uint32_t)t; }
 __device__ __forceinline__ uint32_t trace_smid() { uint32_t v; asm("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
@@ -185,14 +187,21 @@ struct Ticket {
 	}
 };
 
-#ifndef B200GS_FWD_MIN_CTAS
-#define B200GS_FWD_MIN_CTAS 6
+// Two instantiations of each kernel.  WIDE: the alphas of a whole batch of 16 are evaluated before its recurrence (forward) /
+// phase 1 is straight-line code over 8 survivors at a time (backward), ~150-170 registers, 3 CTAs per SM: each warp has several
+// independent chains in flight, which is what a kernel needs whose critical path is its deepest unit -- one warp -- as long as
+// there are only a few units per warp slot (the LLFF shape: 6144 units).  !WIDE: groups of 4 / a loop over survivor pairs, 78-96
+// registers, 6 / 5 CTAs per SM: more warps hide more latency once there are many units per slot (measured at 35k and 65k
+// units: 3-7 % faster than WIDE; at 6144 units WIDE is 14 % / 11 % faster).
+constexpr unsigned WIDE_MAX_UNITS = 16384;
+#ifndef B200GS_FWD_NARROW_CTAS
+#define B200GS_FWD_NARROW_CTAS 6
 #endif
-template <bool EXT>
-__global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_FWD_MIN_CTAS) blend_forward_kernel(
+template <bool EXT, bool WIDE>
+__global__ void __launch_bounds__(BLEND_WARPS * 32, WIDE ? 3 : B200GS_FWD_NARROW_CTAS) blend_forward_kernel(
 	const uint2* ranges, const uint32_t* order, const uint32_t* point_list, const float4* rec,
 	int W, int H, int grid_x, uint32_t units, GeomHeader* hdr, uint4* clean_words, size_t clean_count,
-	uint32_t* surv_bits, size_t surv_words,
+	uint32_t* surv_bits, size_t surv_words, uint32_t* tile_cost,
 	const float* __restrict__ bg, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
 	float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_alpha, float* __restrict__ out_feat)
 {
@@ -224,12 +233,14 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_FWD_MIN_CTAS) blend_f
 #ifdef B200GS_BLEND_TRACE
 		const uint32_t tr_t0 = trace_ns(), tr_c0 = (uint32_t)clock64();
 		int tr_rounds = 0, tr_surv = 0;
+		uint32_t tr_proc = 0, tr_wait = 0, tr_nb = 0;  // (B200GS_BLEND_TRACE=2: exposed latency of the id and geometry loads)
 #endif
 		Walk<true> wk;
 		wk.list = point_list + u.range.x; wk.rec = rec; wk.n = (int)(u.range.y - u.range.x); wk.top = 0; wk.lane = lane;
 		const int R = (wk.n + 31) >> 5;
 		uint32_t* bits = surv_bits + (size_t)u.sub * surv_words + (u.range.x >> 5) + u.tile;  // this unit's survivor-bitmap words
 
+		uint32_t unit_cost = 8;  // what this unit costs, in the schedule builder's units: 4 per round walked + 1 per survivor staged
 		bool done = !u.inside;
 		float T = 1.0f;
 		int lc = -1;                    // ring-absolute index of the last survivor blended into this pixel
@@ -242,43 +253,49 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_FWD_MIN_CTAS) blend_f
 		// (independent), then the recurrence, branch-free: a pair that is skipped or comes after the pixel is saturated
 		// accumulates with weight 0 (exact for finite payloads).  T >= 1e-4 holds while the pixel is live, so a skipped
 		// pair (alpha = 0, test_T == T) can never trip the saturation test.
-		auto group4 = [&](int base, int abs0) {
-			float al[4];
-			bool pos_power[4];
-			float4 cc[4], ff[4];
+		// N (4 or 16) staged survivors at ring slots base.. (front to back, base % N == 0).  First all N alphas -- packed pairs,
+		// independent of each other, so a warp on its own still fills the pipes -- then the N-step recurrence.  Evaluating a
+		// whole batch of 16 before its recurrence is what shortens the deepest units (the kernel's critical path: one warp each,
+		// latency bound): with groups of 4 in a loop every group paid the shared-memory loads, the alpha chain and the
+		// recurrence back to back.
+		auto group = [&](auto NCONST, int base, int abs0) {
+			constexpr int N = decltype(NCONST)::value;
+			constexpr bool EARLY = N <= 4;  // small groups fetch their payload with the geometry (fewer registers are live across the recurrence)
+			float al[N];
+			float4 pc[EARLY ? N : 1], pf[EARLY ? N : 1];
 #pragma unroll
-			for (int h = 0; h < 2; h++) {  // survivors (base + 2h, base + 2h + 1): one packed evaluation
+			for (int h = 0; h < N / 2; h++) {  // survivors (base + 2h, base + 2h + 1): one packed evaluation
 				const GeoPair& gp = S.geo[(base >> 1) + h];
 				const float4 xy = gp.xy, ab = gp.ab, co = gp.co;
-				cc[2 * h] = S.g2[base + 2 * h];
-				cc[2 * h + 1] = S.g2[base + 2 * h + 1];
-				if (EXT) { ff[2 * h] = S.g3[base + 2 * h]; ff[2 * h + 1] = S.g3[base + 2 * h + 1]; }
+				if (EARLY) {
+					pc[2 * h] = S.g2[base + 2 * h]; pc[2 * h + 1] = S.g2[base + 2 * h + 1];
+					if (EXT) { pf[2 * h] = S.g3[base + 2 * h]; pf[2 * h + 1] = S.g3[base + 2 * h + 1]; }
+				}
 				const float2 dx = add2(make_float2(xy.x, xy.y), npx), dy = add2(make_float2(xy.z, xy.w), npy);
 				const float2 power = pair_power2(dx, dy, make_float2(ab.x, ab.y), make_float2(ab.z, ab.w), make_float2(co.x, co.y));
 				const float2 oe = mul2(make_float2(co.z, co.w), expf2(power));
-				al[2 * h] = fminf(0.99f, oe.x);
-				al[2 * h + 1] = fminf(0.99f, oe.y);
-				pos_power[2 * h] = power.x > 0.0f;
-				pos_power[2 * h + 1] = power.y > 0.0f;
+				const float a0 = fminf(0.99f, oe.x), a1 = fminf(0.99f, oe.y);
+				al[2 * h] = (power.x > 0.0f || a0 < 1.0f / 255.0f) ? 0.f : a0;  // 0 <=> skipped pair (forward.cu:336-345)
+				al[2 * h + 1] = (power.y > 0.0f || a1 < 1.0f / 255.0f) ? 0.f : a1;
 			}
-#pragma unroll
-			for (int k = 0; k < 4; k++) al[k] = (pos_power[k] || al[k] < 1.0f / 255.0f) ? 0.f : al[k];  // 0 <=> skipped pair (forward.cu:336-345)
 			int lc_rel = -1;
 #pragma unroll
-			for (int k = 0; k < 4; k++) {
+			for (int k = 0; k < N; k++) {
+				const float4 cc = EARLY ? pc[k] : S.g2[base + k];
 				const float alpha = al[k];
 				const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
 				const bool pdone = done || test_T < 0.0001f;
 				const float Tb = pdone ? 0.f : T;
 				// rgb: the reference's exact sequence fma(T, alpha*c, C) (forward.cu:355), images are bit-identical
-				C01 = fma2(splat2(Tb), mul2(splat2(alpha), make_float2(cc[k].x, cc[k].y)), C01);
-				C2 = __fmaf_rn(Tb, __fmul_rn(alpha, cc[k].z), C2);
+				C01 = fma2(splat2(Tb), mul2(splat2(alpha), make_float2(cc.x, cc.y)), C01);
+				C2 = __fmaf_rn(Tb, __fmul_rn(alpha, cc.z), C2);
 				if (EXT) {
+					const float4 ff = EARLY ? pf[k] : S.g3[base + k];
 					const float wt = __fmul_rn(alpha, Tb);
-					C3 = __fmaf_rn(wt, cc[k].w, C3);
+					C3 = __fmaf_rn(wt, cc.w, C3);
 					C4 = __fadd_rn(C4, wt);
-					C56 = fma2(splat2(wt), make_float2(ff[k].x, ff[k].y), C56);
-					C7 = __fmaf_rn(wt, ff[k].z, C7);
+					C56 = fma2(splat2(wt), make_float2(ff.x, ff.y), C56);
+					C7 = __fmaf_rn(wt, ff.z, C7);
 				}
 				lc_rel = (!pdone && alpha != 0.f) ? k : lc_rel;
 				T = pdone ? T : test_T;
@@ -286,11 +303,18 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_FWD_MIN_CTAS) blend_f
 			}
 			lc = lc_rel >= 0 ? abs0 + lc_rel : lc;
 		};
-		// groups [tail, tail + 4*ngroups): tail is a multiple of 16 (or of 4 in the final flush), so a group never wraps
+		// a full batch [tail, tail + 16) (tail % 16 == 0) / the final flush's groups of 4 [tail, tail + 4 * ngroups)
+		constexpr int GROUP = WIDE ? BATCH : 4;
+		auto process_batch = [&](int tail) {
+#pragma unroll 1
+			for (int j = 0; j < BATCH; j += GROUP)  // (one pass when WIDE; the narrow variant must not unroll: registers)
+				group(std::integral_constant<int, GROUP>{}, (tail & (RING - 1)) + j, tail + j);
+			if (lc >= tail) last_contributor = S.pos[lc & (RING - 1)];  // before the slot can be recycled
+		};
 		auto process = [&](int tail, int ngroups) {
 			const int base0 = tail & (RING - 1);
-			for (int j = 0; j < ngroups; j++) group4(base0 + 4 * j, tail + 4 * j);
-			if (lc >= tail) last_contributor = S.pos[lc & (RING - 1)];  // before the slot can be recycled
+			for (int j = 0; j < ngroups; j++) group(std::integral_constant<int, 4>{}, base0 + 4 * j, tail + 4 * j);
+			if (lc >= tail) last_contributor = S.pos[lc & (RING - 1)];
 		};
 
 		if (R > 0) {
@@ -305,19 +329,31 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_FWD_MIN_CTAS) blend_f
 			for (int j = 0; j <= K_INFLIGHT; j++) hist[j] = 0;
 			bool all_done = false;
 			for (int r = 0; r < R; r++) {
+#if defined(B200GS_BLEND_TRACE) && B200GS_BLEND_TRACE == 2
+				const uint32_t lt0 = (uint32_t)clock64();
+#endif
 				const uint32_t idd = wk.load_id(r + 3);            // ids, round r+3
+#if defined(B200GS_BLEND_TRACE) && B200GS_BLEND_TRACE == 2
+				asm volatile("" ::"r"(idd) : "memory");
+				const uint32_t lt1 = (uint32_t)clock64();
+#endif
 				float4 gc0 = make_float4(0.f, 0.f, 0.f, 0.f), gc1 = gc0;
 				wk.load_geo(idc, gc0, gc1);                        // geometry, round r+2
+#if defined(B200GS_BLEND_TRACE) && B200GS_BLEND_TRACE == 2
+				asm volatile("" ::"f"(gc0.x), "f"(gc1.x) : "memory");
+				{ const uint32_t lt2 = (uint32_t)clock64(); tr_proc += lt1 - lt0; tr_wait += lt2 - lt1; tr_nb++; }
+#endif
 				cp_wait<K_INFLIGHT>();  // every group but the latest K has landed: survivors of rounds <= r-1-K are complete
 				if (hist[K_INFLIGHT] - tail >= BATCH || head - tail > RING - 32) {
 					if (head - tail > RING - 32) { cp_wait<0>(); hist[K_INFLIGHT] = head; }  // a dense stretch: make room for a full round
 					__syncwarp();
-					do { process(tail, BATCH / 4); tail += BATCH; } while (hist[K_INFLIGHT] - tail >= BATCH);
+					do { process_batch(tail); tail += BATCH; } while (hist[K_INFLIGHT] - tail >= BATCH);
 					__syncwarp();
 					all_done = __all_sync(0xFFFFFFFFu, done);
 					if (all_done) break;
 				}
 				head += wk.template stage<EXT>(S, r, ida, ga0, ga1, u.pb, head, bits);
+				unit_cost = 8u + 4u * (uint32_t)(r + 1) + (uint32_t)head;
 #ifdef B200GS_BLEND_TRACE
 				tr_rounds = r + 1; tr_surv = head;
 #endif
@@ -350,8 +386,10 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_FWD_MIN_CTAS) blend_f
 			}
 			__syncwarp();  // the ring is reused by the next unit
 		}
+		if (tile_cost && lane == 0) atomicAdd(tile_cost + u.tile, unit_cost);
 #ifdef B200GS_BLEND_TRACE
 		trace_put(0, unit, tr_t0, tr_c0, wk.n, tr_rounds, tr_surv);
+		if (lane == 0 && unit < (1u << 16)) { g_trace2[unit][0] = tr_proc; g_trace2[unit][1] = tr_wait; g_trace2[unit][2] = 0; g_trace2[unit][3] = tr_nb; }
 #endif
 		if (u.inside) {
 			const size_t pix = (size_t)u.py * W + u.px, HW = (size_t)H * W;
@@ -372,14 +410,11 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_FWD_MIN_CTAS) blend_f
 	tk.leave(lane, gridDim.x * BLEND_WARPS);
 }
 
-#ifndef B200GS_BWD_MIN_CTAS
-#define B200GS_BWD_MIN_CTAS 5  // shared memory allows 5 CTAs/SM; stating it lets ptxas use 96 registers instead of 72 (measured: -3 us)
-#endif
-template <bool EXT>
-__global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_BWD_MIN_CTAS) blend_backward_kernel(
+template <bool EXT, bool WIDE>
+__global__ void __launch_bounds__(BLEND_WARPS * 32, WIDE ? 3 : 5) blend_backward_kernel(
 	const uint2* ranges, const uint32_t* order, const uint32_t* point_list, const float4* rec,
 	int W, int H, int grid_x, uint32_t units, unsigned int* ticket, unsigned int* exits,
-	const uint32_t* surv_bits, size_t surv_words,
+	const uint32_t* surv_bits, size_t surv_words, uint32_t* tile_cost,
 	const float* __restrict__ bg, const float* final_T, const uint32_t* n_contrib, const float* __restrict__ dL_dcolor,
 	const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dalpha_map, const float* __restrict__ dL_dfeat,
 	float* __restrict__ grec)
@@ -394,6 +429,7 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_BWD_MIN_CTAS) blend_b
 	const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
 	const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
 	const Ticket tk{ticket, exits};
+	const uint32_t gridDim_tiles = units >> 3;  // tiles of the image: the backward's costs are the second plane of tile_cost
 	{  // pixel-moment half of the basis table: the same for every unit
 		const float cx = (float)(lane & 7), cy = (float)(lane >> 3);
 		S.basis[lane][0][0] = make_float4(1.f, cx, cy, cx * cx);
@@ -440,10 +476,63 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_BWD_MIN_CTAS) blend_b
 
 		// One batch: `count` staged survivors at ring slots base.. (base % 16 == 0), deepest first; `cpad` = count rounded
 		// up to even (an odd tail is padded with an inert survivor).
-		auto process = [&](int base, int count, int cpad) {
+		auto process = [&](auto FULLC, int base, int count, int cpad) {
+			constexpr bool FULL = decltype(FULLC)::value && WIDE;  // a whole batch of 16: phase 1 is straight-line code
 			// ---- phase 1: lane = pixel.  The reference's per-channel accum_rec recurrence (backward.cu:509-516) is
 			// carried as one scalar, A = sum_ch accum_rec[ch] * dL/dpixel[ch].
 			float* wrow = &S.w[0][lane * WSTRIDE];
+			if (FULL) {
+				// Everything that does not depend on the running T and A -- G, alpha, 1/(1-alpha), the channel dot product D -- is
+				// evaluated for eight survivors at a time (independent chains: a warp on its own still fills the pipes), then the
+				// eight recurrence steps follow branch-free.  The deepest units are the kernel's critical path and each is one warp.
+#pragma unroll
+				for (int half = 0; half < 2; half++) {
+					float al[8], inv[8], Dk[8], og[8];
+					bool act[8];
+#pragma unroll
+					for (int k = 0; k < 8; k++) {
+						const int sl = base + 8 * half + k;
+						const float4 a = S.g0[sl];
+						const float4 b = S.g1[sl];
+						const float dx = __fsub_rn(a.x, u.pxf), dy = __fsub_rn(a.y, u.pyf);
+						const float pw = pair_power(dx, dy, a.z, a.w, b.x);
+						const float G = exp_fast(pw);
+						al[k] = fminf(0.99f, __fmul_rn(b.y, G));
+						act[k] = (S.pos[sl] <= last_contributor) && !(pw > 0.0f) && !(al[k] < 1.0f / 255.0f);
+						inv[k] = rcp_approx(1.0f - al[k]);
+						og[k] = G * b.y;
+						const float4 c = S.g2[sl];
+						if (EXT) {
+							const float4 f = S.g3[sl];
+							float2 Dp = mul2(make_float2(c.x, c.y), d01);
+							Dp = fma2(make_float2(c.z, c.w), d23, Dp);
+							Dp = fma2(make_float2(f.x, f.y), d56, Dp);
+							Dk[k] = (Dp.x + Dp.y) + fmaf(f.z, dpix[7], dpix[4]);
+						} else {
+							Dk[k] = c.x * dpix[0] + c.y * dpix[1] + c.z * dpix[2];
+						}
+					}
+#pragma unroll
+					for (int k = 0; k < 8; k += 2) {
+						float wgs[2], wcs[2];
+#pragma unroll
+						for (int q = 0; q < 2; q++) {
+							const int i = k + q;
+							const float Tn = T * inv[i];
+							const float An = fmaf(1.f - last_alpha, A, last_alpha * lastD);
+							const float dL_dalpha = (Dk[i] - An) * Tn - (T_final * inv[i]) * bg_dot_dpixel;
+							wgs[q] = act[i] ? og[i] * dL_dalpha : 0.f;  // G * dL/dG; clamp ignored as in backward.cu:538
+							wcs[q] = act[i] ? al[i] * Tn : 0.f;
+							T = act[i] ? Tn : T;
+							A = act[i] ? An : A;
+							lastD = act[i] ? Dk[i] : lastD;
+							last_alpha = act[i] ? al[i] : last_alpha;
+						}
+						*reinterpret_cast<float2*>(wrow + 8 * half + k) = make_float2(wgs[0], wgs[1]);
+						*reinterpret_cast<float2*>(wrow + 32 * WSTRIDE + 16 + 8 * half + k) = make_float2(wcs[0], wcs[1]);  // S.w[1]
+					}
+				}
+			} else
 			for (int k0 = 0; k0 < cpad; k0 += 2) {
 				float Gk[2], op[2], pw[2], al[2];
 #pragma unroll
@@ -580,7 +669,7 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_BWD_MIN_CTAS) blend_b
 			if (hist[K_INFLIGHT] - tail >= BATCH || head - tail > RING - 32) {
 				if (head - tail > RING - 32) { cp_wait<0>(); hist[K_INFLIGHT] = head; }
 				__syncwarp();
-				do { process(tail & (RING - 1), BATCH, BATCH); tail += BATCH; } while (hist[K_INFLIGHT] - tail >= BATCH);
+				do { process(std::true_type{}, tail & (RING - 1), BATCH, BATCH); tail += BATCH; } while (hist[K_INFLIGHT] - tail >= BATCH);
 			}
 			head += stage(r, ida, head);
 			cp_commit();
@@ -602,10 +691,11 @@ __global__ void __launch_bounds__(BLEND_WARPS * 32, B200GS_BWD_MIN_CTAS) blend_b
 			__syncwarp();
 			while (head > tail) {
 				const int c = min(BATCH, head - tail);
-				process(tail & (RING - 1), c, (c + 1) & ~1);
+				process(std::false_type{}, tail & (RING - 1), c, (c + 1) & ~1);
 				tail += c;
 			}
 		}
+		if (tile_cost && lane == 0) atomicAdd(tile_cost + (size_t)gridDim_tiles + u.tile, 16u + (uint32_t)R + (uint32_t)head);
 #ifdef B200GS_BLEND_TRACE
 		trace_put(1, unit, tr_t0, tr_c0, wk.n, R, head);
 #endif
@@ -659,15 +749,54 @@ cudaError_t launch_blend(unsigned site, void (*kernel)(KArgs...), unsigned grid,
 }  // namespace
 
 #ifdef B200GS_BLEND_TRACE
+extern "C" int b200gs_debug_blend_trace2(uint32_t* host_out) {
+	return (int)cudaMemcpyFromSymbol(host_out, g_trace2, sizeof(uint32_t) * (1 << 16) * 4, 0);
+}
 extern "C" int b200gs_debug_blend_trace(uint32_t* host_out, int dir) {
 	return (int)cudaMemcpyFromSymbol(host_out, g_trace, sizeof(uint32_t) * (1 << 16) * 8, (size_t)dir * sizeof(uint32_t) * (1 << 16) * 8);
 }
 #endif
 
+namespace {
+bool use_wide(unsigned units) {
+	static int forced = -2;
+	if (forced == -2) { const char* e = getenv("B200GS_BLEND_WIDE"); forced = e ? atoi(e) : -1; }  // 0 / 1: A/B runs
+	return forced >= 0 ? forced != 0 : units <= WIDE_MAX_UNITS;
+}
+template <bool EXT, bool WIDE>
+void forward_variant(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is, const b200gs_outputs_t& out, cudaStream_t stream,
+                     uint4* clean_words, size_t clean_count, uint32_t* cost, int gx, unsigned units) {
+	static unsigned cap = 0;
+	constexpr size_t smem = BLEND_WARPS * sizeof(FwdSmem<EXT>);
+	if (!cap) cap = persistent_cap(blend_forward_kernel<EXT, WIDE>, smem, ctas_per_sm(0));
+	const unsigned want = (units + BLEND_WARPS - 1) / BLEND_WARPS;
+	launch_blend(PDL_BLEND_FWD, blend_forward_kernel<EXT, WIDE>, want < cap ? want : cap, smem, stream, (const uint2*)is.ranges,
+		(const uint32_t*)is.tile_order, (const uint32_t*)bs.sorted_vals, (const float4*)gs.rec,
+		v.width, v.height, gx, units, gs.hdr, clean_words, clean_count, bs.surv_bits, bs.surv_words, cost, v.background, is.final_T, is.n_contrib,
+		out.color, EXT ? out.depth : (float*)nullptr, EXT ? out.alpha : (float*)nullptr, EXT ? out.feature : (float*)nullptr);
+}
+template <bool EXT, bool WIDE>
+void backward_variant(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is, const b200gs_grad_outputs_t& gout, float* grec,
+                      cudaStream_t stream, uint32_t* cost, int gx, unsigned units) {
+	static unsigned cap = 0;
+	constexpr size_t smem = BLEND_WARPS * sizeof(BwdSmem<EXT>);
+	if (!cap) cap = persistent_cap(blend_backward_kernel<EXT, WIDE>, smem, ctas_per_sm(1));
+	const unsigned want = (units + BLEND_WARPS - 1) / BLEND_WARPS;
+	// first kernel of the backward chain: its predecessor is a memset / the caller's loss kernels, so no programmatic launch
+	launch_blend(0u, blend_backward_kernel<EXT, WIDE>, want < cap ? want : cap, smem, stream, (const uint2*)is.ranges,
+		(const uint32_t*)is.tile_order_bwd, (const uint32_t*)bs.sorted_vals, (const float4*)gs.rec,
+		v.width, v.height, gx, units, &gs.hdr->blend_ticket[1], &gs.hdr->blend_exit[1], (const uint32_t*)bs.surv_bits, bs.surv_words, cost, v.background,
+		(const float*)is.final_T, (const uint32_t*)is.n_contrib, gout.dL_dcolor, EXT ? gout.dL_ddepth : (const float*)nullptr,
+		EXT ? gout.dL_dalpha : (const float*)nullptr, EXT ? gout.dL_dfeature : (const float*)nullptr, grec);
+}
+}  // namespace
+
 void launch_blend_forward(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
-                          const b200gs_outputs_t& out, cudaStream_t stream, uint4* clean_words, size_t clean_count) {
+                          const b200gs_outputs_t& out, cudaStream_t stream, uint4* clean_words, size_t clean_count, bool history) {
+	uint32_t* cost = history ? is.tile_cost : nullptr;
 	const int gx = (v.width + TILE_X - 1) / TILE_X, gy = (v.height + TILE_Y - 1) / TILE_Y;
 	unsigned units = (unsigned)(gx * gy * 8);
+	const bool wide = use_wide(units);
 #ifdef B200GS_BLEND_TRACE
 	if (const char* e = getenv("B200GS_BLEND_UNIT_RANGE")) {
 		unsigned lo = 0, hi = units;
@@ -675,50 +804,27 @@ void launch_blend_forward(const b200gs_view_t& v, GeomState& gs, BinningState& b
 	}
 #endif
 	if (v.extended) {
-		static unsigned cap = 0;
-		constexpr size_t smem = BLEND_WARPS * sizeof(FwdSmem<true>);
-		if (!cap) cap = persistent_cap(blend_forward_kernel<true>, smem, ctas_per_sm(0));
-		const unsigned want = (units + BLEND_WARPS - 1) / BLEND_WARPS;
-		launch_blend(PDL_BLEND_FWD, blend_forward_kernel<true>, want < cap ? want : cap, smem, stream, (const uint2*)is.ranges,
-			(const uint32_t*)is.tile_order, (const uint32_t*)bs.sorted_vals, (const float4*)gs.rec,
-			v.width, v.height, gx, units, gs.hdr, clean_words, clean_count, bs.surv_bits, bs.surv_words, v.background, is.final_T, is.n_contrib, out.color, out.depth, out.alpha, out.feature);
+		if (wide) forward_variant<true, true>(v, gs, bs, is, out, stream, clean_words, clean_count, cost, gx, units);
+		else forward_variant<true, false>(v, gs, bs, is, out, stream, clean_words, clean_count, cost, gx, units);
 	} else {
-		static unsigned cap = 0;
-		constexpr size_t smem = BLEND_WARPS * sizeof(FwdSmem<false>);
-		if (!cap) cap = persistent_cap(blend_forward_kernel<false>, smem, ctas_per_sm(0));
-		const unsigned want = (units + BLEND_WARPS - 1) / BLEND_WARPS;
-		launch_blend(PDL_BLEND_FWD, blend_forward_kernel<false>, want < cap ? want : cap, smem, stream, (const uint2*)is.ranges,
-			(const uint32_t*)is.tile_order, (const uint32_t*)bs.sorted_vals, (const float4*)gs.rec,
-			v.width, v.height, gx, units, gs.hdr, clean_words, clean_count, bs.surv_bits, bs.surv_words, v.background, is.final_T, is.n_contrib, out.color, (float*)nullptr, (float*)nullptr, (float*)nullptr);
+		if (wide) forward_variant<false, true>(v, gs, bs, is, out, stream, clean_words, clean_count, cost, gx, units);
+		else forward_variant<false, false>(v, gs, bs, is, out, stream, clean_words, clean_count, cost, gx, units);
 	}
 	count_launch();
 }
 
 void launch_blend_backward(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
-                           const b200gs_grad_outputs_t& gout, float* grec, cudaStream_t stream) {
+                           const b200gs_grad_outputs_t& gout, float* grec, cudaStream_t stream, bool history) {
+	uint32_t* cost = history ? is.tile_cost : nullptr;
 	const int gx = (v.width + TILE_X - 1) / TILE_X, gy = (v.height + TILE_Y - 1) / TILE_Y;
 	const unsigned units = (unsigned)(gx * gy * 8);
-	unsigned int* ticket = &gs.hdr->blend_ticket[1];
-	unsigned int* exits = &gs.hdr->blend_exit[1];
-	// first kernel of the backward chain: its predecessor is a memset / the caller's loss kernels, so no programmatic launch
+	const bool wide = use_wide(units);
 	if (v.extended) {
-		static unsigned cap = 0;
-		constexpr size_t smem = BLEND_WARPS * sizeof(BwdSmem<true>);
-		if (!cap) cap = persistent_cap(blend_backward_kernel<true>, smem, ctas_per_sm(1));
-		const unsigned want = (units + BLEND_WARPS - 1) / BLEND_WARPS;
-		launch_blend(0u, blend_backward_kernel<true>, want < cap ? want : cap, smem, stream, (const uint2*)is.ranges,
-			(const uint32_t*)is.tile_order, (const uint32_t*)bs.sorted_vals, (const float4*)gs.rec,
-			v.width, v.height, gx, units, ticket, exits, (const uint32_t*)bs.surv_bits, bs.surv_words, v.background, (const float*)is.final_T, (const uint32_t*)is.n_contrib,
-			gout.dL_dcolor, gout.dL_ddepth, gout.dL_dalpha, gout.dL_dfeature, grec);
+		if (wide) backward_variant<true, true>(v, gs, bs, is, gout, grec, stream, cost, gx, units);
+		else backward_variant<true, false>(v, gs, bs, is, gout, grec, stream, cost, gx, units);
 	} else {
-		static unsigned cap = 0;
-		constexpr size_t smem = BLEND_WARPS * sizeof(BwdSmem<false>);
-		if (!cap) cap = persistent_cap(blend_backward_kernel<false>, smem, ctas_per_sm(1));
-		const unsigned want = (units + BLEND_WARPS - 1) / BLEND_WARPS;
-		launch_blend(0u, blend_backward_kernel<false>, want < cap ? want : cap, smem, stream, (const uint2*)is.ranges,
-			(const uint32_t*)is.tile_order, (const uint32_t*)bs.sorted_vals, (const float4*)gs.rec,
-			v.width, v.height, gx, units, ticket, exits, (const uint32_t*)bs.surv_bits, bs.surv_words, v.background, (const float*)is.final_T, (const uint32_t*)is.n_contrib,
-			gout.dL_dcolor, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, grec);
+		if (wide) backward_variant<false, true>(v, gs, bs, is, gout, grec, stream, cost, gx, units);
+		else backward_variant<false, false>(v, gs, bs, is, gout, grec, stream, cost, gx, units);
 	}
 	count_launch();
 }

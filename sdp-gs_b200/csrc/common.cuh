@@ -58,6 +58,12 @@ struct ImageState {
 	uint2* ranges;         // [tiles]
 	uint32_t* tile_order;  // [tiles] tile ids, heaviest (longest range) first: launch order of the blend units
 	uint32_t* tile_count;  // [tiles] instances per tile, counted while they are emitted (zeroed by the preprocess kernel)
+	// Persistent workspaces only (a session renders the same view again and again): what the blend units of each tile cost the
+	// last time -- [0][t] forward, [1][t] backward, in units of (rounds walked, survivors blended) -- accumulated by the blend
+	// kernels and consumed (and zeroed) by the next call's schedule builder, which then orders the tiles by measured cost
+	// instead of list length (the two correlate poorly: long lists saturate early).  Zero = no history.
+	uint32_t* tile_cost;       // [2][tiles]
+	uint32_t* tile_order_bwd;  // [tiles] launch order of the backward's units
 	size_t bytes;
 };
 
@@ -116,17 +122,18 @@ bool tile_counts_path(int tiles);  // scan_emit also produces tile ranges + blen
 int tile_count_stride();
 void launch_depth_order(GeomState& gs, int P, cudaStream_t stream);                     // stable sort of Gaussian ids by depth bits
 void launch_scan_emit(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is, int P, int64_t capacity, cudaStream_t stream,
-                      bool chained /* the previous kernel in the stream is our depth sort */);
+                      bool chained /* the previous kernel in the stream is our depth sort */, bool history /* order the blend units by ImageState::tile_cost */);
 void launch_tile_sort(const b200gs_view_t& v, GeomState& gs, BinningState& bs, int64_t capacity, cudaStream_t stream);
-void launch_tile_ranges(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is, int64_t capacity, cudaStream_t stream);
+void launch_tile_ranges(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is, int64_t capacity, cudaStream_t stream, bool history);
 void launch_debug_keys(const b200gs_view_t& v, GeomState& gs, BinningState& bs, uint64_t* keys_out, int64_t L,
                        cudaStream_t stream);
 
 void launch_blend_forward(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
-                          const b200gs_outputs_t& out, cudaStream_t stream, uint4* clean_words, size_t clean_count);  // also writes bs.surv_bits
+                          const b200gs_outputs_t& out, cudaStream_t stream, uint4* clean_words, size_t clean_count,
+                          bool history /* record the units' cost in ImageState::tile_cost */);  // also writes bs.surv_bits
 void launch_finalize_header(GeomState& gs, int64_t capacity, cudaStream_t stream);
 void launch_blend_backward(const b200gs_view_t& v, GeomState& gs, BinningState& bs, ImageState& is,
-                           const b200gs_grad_outputs_t& gout, float* grec, cudaStream_t stream);
+                           const b200gs_grad_outputs_t& gout, float* grec, cudaStream_t stream, bool history);
 
 // ---- device helpers ----
 #ifdef __CUDACC__
