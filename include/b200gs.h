@@ -74,6 +74,11 @@ typedef struct b200gs_gaussians {
 	const float* shs_language;             /* [P,3] degree-0 SH of the feature head, or NULL; feature =
 	                                          normalize(C0*shs_language) as gaussian_renderer/__init__.py:283-287 */
 	const float* confidence;               /* [P,1] or NULL (== all ones); multiplies opacity, no gradient */
+	/* Optional (NULL: all P rows are Gaussians).  Device word holding the number of live rows: rows >= *live_count are
+	 * treated as culled (radius 0, no instances, zero gradients).  For capacity-sized parameter buffers whose Gaussian count
+	 * changes on the device (densify / prune, scene/gaussian_model.py:400-608) while P, the launch geometry and any CUDA
+	 * graph that captured this call stay fixed. */
+	const uint32_t* live_count;
 } b200gs_gaussians_t;
 
 typedef struct b200gs_outputs {

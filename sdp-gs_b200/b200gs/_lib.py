@@ -32,6 +32,7 @@ class Gaussians(C.Structure):
         ("means3D", C.c_void_p), ("shs", C.c_void_p), ("colors_precomp", C.c_void_p), ("opacities", C.c_void_p),
         ("scales", C.c_void_p), ("rotations", C.c_void_p), ("cov3D_precomp", C.c_void_p),
         ("language_feature_precomp", C.c_void_p), ("shs_language", C.c_void_p), ("confidence", C.c_void_p),
+        ("live_count", C.c_void_p),
     ]
 
 

@@ -416,7 +416,10 @@ class RasterSession:
 
     def __init__(self, raster_settings, *, means3D, opacities, shs=None, colors_precomp=None, scales=None,
                  rotations=None, cov3D_precomp=None, shs_language=None, language_feature_precomp=None,
-                 extended=False, capacity, grads_out=None, with_backward=True, grad_scatter=None):
+                 extended=False, capacity, grads_out=None, with_backward=True, grad_scatter=None, live_count=None):
+        """live_count: optional uint32/int32 device tensor of one element -- the number of live rows of capacity-sized
+        parameter buffers (b200gs_gaussians_t.live_count); rows past it are culled, so the Gaussian count can change on the
+        device without touching this session or its captured graph."""
         rs = raster_settings
         self.rs, self.extended, self.capacity = rs, bool(extended), int(capacity)
         dev = means3D.device
@@ -438,6 +441,11 @@ class RasterSession:
         g.means3D, g.shs, g.colors_precomp, g.opacities = _ptr(i["means3D"]), _ptr(i["shs"]), _ptr(i["colors_precomp"]), _ptr(i["opacities"])
         g.scales, g.rotations, g.cov3D_precomp = _ptr(i["scales"]), _ptr(i["rotations"]), _ptr(i["cov3D_precomp"])
         g.language_feature_precomp, g.shs_language, g.confidence = _ptr(i["language_feature_precomp"]), _ptr(i["shs_language"]), _ptr(i["confidence"])
+        if live_count is not None:
+            if live_count.device != dev or live_count.numel() != 1 or live_count.dtype not in (torch.int32, torch.uint32):
+                raise RuntimeError("live_count must be a one-element int32/uint32 tensor on the session's device")
+            self._keep.append(live_count)
+            g.live_count = live_count.data_ptr()
         self.v = _build_view(rs, P, M, self.extended, self._keep)
         f32 = dict(dtype=torch.float32, device=dev)
         self.color = torch.empty((3, H, W), **f32)

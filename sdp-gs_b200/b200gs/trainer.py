@@ -33,7 +33,8 @@ from .schedule import DEFAULTS, expon_lr  # noqa: E402,F401  (pure Python: impor
 
 class GaussianTrainer:
     def __init__(self, *, xyz, shs, opacity_raw, scaling_raw, rotation_raw, feature, cameras, gt_images, depth_mono,
-                 device, capacity, sh_degree=3, active_sh_degree=None, background=None, hparams=None, settings_fn=None):
+                 device, capacity, sh_degree=3, active_sh_degree=None, background=None, hparams=None, settings_fn=None,
+                 gaussian_capacity=None):
         dev = torch.device(device)
         self.dev = dev
         f32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32) if isinstance(a, np.ndarray) else a,
@@ -58,6 +59,9 @@ class GaussianTrainer:
         self.scratch = torch.empty((lib.b200gs_photometric_scratch_bytes(W, H) // 4,), dtype=torch.float32, device=dev)
         self.iteration = 0
         self.capacity = capacity
+        # rows of the per-Gaussian buffers (>= the Gaussian count).  None: exactly the count; densify_and_prune then re-allocates
+        # with head-room the first time the count grows and works in place from there on (no re-allocation, no graph re-capture).
+        self.gaussian_capacity = gaussian_capacity
         self.settings_fn = settings_fn or self._default_settings
         self.widths = dict(xyz=3, shs=48, opacity=1, scaling=3, rotation=4, feature=3)
         P = int(xyz.shape[0])
@@ -66,46 +70,75 @@ class GaussianTrainer:
         self.set_hparams(step=1)
         self._refresh_activations()
 
-    def _allocate(self, raw, m=None, v=None):
+    def _allocate(self, raw, m=None, v=None, rows=None):
         """(Re)build every per-Gaussian buffer for the given raw parameters (and Adam moments): flat parameter / moment
-        allocations, activated copies, the fused gradient buffer and one RasterSession per view."""
+        allocations of `rows` >= P rows, activated copies, the fused gradient buffer and one RasterSession per view.  The kernels
+        always run over all `rows`; the Gaussian count lives in a device word (`self.live`, b200gs_gaussians_t.live_count) and
+        the spare rows are inert: culled by the preprocess kernel, zero gradients, zero moments."""
         dev = self.dev
-        P = self.P = int(raw["xyz"].shape[0])
-        Pp = (P + 3) // 4 * 4  # segment stride: 16-byte aligned segments for any P (128-bit accesses, TMA bulk copies)
+        P = int(raw["xyz"].shape[0])
+        Pc = self.Pcap = max(P, int(rows or 0), int(self.gaussian_capacity or 0))
+        Pp = (Pc + 3) // 4 * 4  # segment stride: 16-byte aligned segments for any count (128-bit accesses, TMA bulk copies)
         self.raw_flat = torch.zeros((Pp * 62,), dtype=torch.float32, device=dev)
         self.m_flat = torch.zeros_like(self.raw_flat)
         self.v_flat = torch.zeros_like(self.raw_flat)
-        self.raw, self.m, self.v = {}, {}, {}
+        self._cap = dict(raw={}, m={}, v={})  # capacity-sized views [Pcap, w]
         c = 0
         for k, w in self.widths.items():
-            for store, flat in ((self.raw, self.raw_flat), (self.m, self.m_flat), (self.v, self.v_flat)):
-                store[k] = flat[c * Pp:c * Pp + w * P].view(P, w)
+            for store, flat in ((self._cap["raw"], self.raw_flat), (self._cap["m"], self.m_flat), (self._cap["v"], self.v_flat)):
+                store[k] = flat[c * Pp:c * Pp + w * Pc].view(Pc, w)
             c += w
-        for k in self.widths:
-            self.raw[k].copy_(raw[k].reshape(P, self.widths[k]))
-            if m is not None:
-                self.m[k].copy_(m[k].reshape(P, self.widths[k])); self.v[k].copy_(v[k].reshape(P, self.widths[k]))
-        self.act = dict(opacity=torch.empty((P, 1), dtype=torch.float32, device=dev),
-                        scaling=torch.empty((P, 3), dtype=torch.float32, device=dev),
-                        rotation=torch.empty((P, 4), dtype=torch.float32, device=dev))
-        self.bucket = parallel.FusedGradBuffer(P, dev)
-        self.g_means2D = torch.zeros((P, 3), dtype=torch.float32, device=dev)
+        self.live = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.act = dict(opacity=torch.empty((Pc, 1), dtype=torch.float32, device=dev),
+                        scaling=torch.empty((Pc, 3), dtype=torch.float32, device=dev),
+                        rotation=torch.empty((Pc, 4), dtype=torch.float32, device=dev))
+        self.bucket = parallel.FusedGradBuffer(Pc, dev)
+        self.g_means2D = torch.zeros((Pc, 3), dtype=torch.float32, device=dev)
+        self._write_rows(raw, m, v, P_before=0)
+        C_ = self._cap["raw"]
         grads_out = dict(means3D=self.bucket.segment("xyz"), shs=self.bucket.segment("shs"), opacities=self.bucket.segment("opacity"),
                          scales=self.bucket.segment("scaling"), rotations=self.bucket.segment("rotation"),
                          shs_language=self.bucket.segment("language_feature"), means2D=self.g_means2D)
         self._scatter = self.bucket.scatter_descriptor()
         self.sessions = []
         for cam in self.cameras:
-            s = rz.RasterSession(self.settings_fn(cam), means3D=self.raw["xyz"], opacities=self.act["opacity"],
-                                 shs=self.raw["shs"].view(P, 16, 3), scales=self.act["scaling"], rotations=self.act["rotation"],
-                                 shs_language=self.raw["feature"], extended=True, capacity=self.capacity, grads_out=grads_out,
-                                 grad_scatter=self.bucket.scatter_descriptor())
+            s = rz.RasterSession(self.settings_fn(cam), means3D=C_["xyz"], opacities=self.act["opacity"],
+                                 shs=C_["shs"].view(Pc, 16, 3), scales=self.act["scaling"], rotations=self.act["rotation"],
+                                 shs_language=C_["feature"], extended=True, capacity=self.capacity, grads_out=grads_out,
+                                 grad_scatter=self.bucket.scatter_descriptor(), live_count=self.live)
             self.sessions.append(s)
         self.graphs = None
         self.pair_graphs = {}
         self.pseudo_sessions = []
         if getattr(self, "pseudo_cameras", None):
             self._build_pseudo_sessions()
+
+    def _write_rows(self, raw, m, v, P_before):
+        """Install `raw` (and the moments; None = zeros) as rows [0, P) of the capacity-sized buffers, make rows [P, P_before)
+        inert again, publish the new count.  Everything is stream-ordered device work: no allocation, no synchronization."""
+        P = self.P = int(raw["xyz"].shape[0])
+        assert P <= self.Pcap
+        for k, w in self.widths.items():
+            for name, src in (("raw", raw), ("m", m), ("v", v)):
+                dst = self._cap[name][k]
+                if src is None:
+                    dst[:max(P, P_before)].zero_()
+                else:
+                    dst[:P].copy_(src[k].reshape(P, w))
+                    if P_before > P:
+                        dst[P:P_before].zero_()
+        if P_before > P:
+            self._cap["raw"]["rotation"][P:P_before, 0] = 1.0  # a unit quaternion: the spare rows' activations stay finite
+        elif P_before == 0 and self.Pcap > P:
+            self._cap["raw"]["rotation"][P:, 0] = 1.0
+        self.live.fill_(P)
+        self.raw = {k: t[:P] for k, t in self._cap["raw"].items()}  # live rows, [P, w]
+        self.m = {k: t[:P] for k, t in self._cap["m"].items()}
+        self.v = {k: t[:P] for k, t in self._cap["v"].items()}
+
+    def _stat(self, name):
+        """live rows of a densification statistic (xyz_gradient_accum, denom: [P,1]; max_radii2D: [P])"""
+        return (self.bucket.max_radii2D if name == "max_radii2D" else self.bucket.segment(name))[:self.P]
 
     # ------------------------------------------------------------------ pseudo views (train.py:138-153)
     def add_pseudo_views(self, cameras, depth_refs):
@@ -120,15 +153,16 @@ class GaussianTrainer:
         self._build_pseudo_sessions()
 
     def _build_pseudo_sessions(self):
-        P = self.P
+        P = self.Pcap
+        C_ = self._cap["raw"]
         self.g_means2D_pseudo = torch.zeros((P, 3), dtype=torch.float32, device=self.dev)  # not a densification input (train.py:220-221)
         grads_out = dict(means3D=self.bucket.segment("xyz"), shs=self.bucket.segment("shs"), opacities=self.bucket.segment("opacity"),
                          scales=self.bucket.segment("scaling"), rotations=self.bucket.segment("rotation"),
                          shs_language=self.bucket.segment("language_feature"), means2D=self.g_means2D_pseudo)
-        self.pseudo_sessions = [rz.RasterSession(self.settings_fn(cam), means3D=self.raw["xyz"], opacities=self.act["opacity"],
-                                                 shs=self.raw["shs"].view(P, 16, 3), scales=self.act["scaling"], rotations=self.act["rotation"],
-                                                 shs_language=self.raw["feature"], extended=True, capacity=self.capacity, grads_out=grads_out,
-                                                 grad_scatter=self.bucket.scatter_descriptor())
+        self.pseudo_sessions = [rz.RasterSession(self.settings_fn(cam), means3D=C_["xyz"], opacities=self.act["opacity"],
+                                                 shs=C_["shs"].view(P, 16, 3), scales=self.act["scaling"], rotations=self.act["rotation"],
+                                                 shs_language=C_["feature"], extended=True, capacity=self.capacity, grads_out=grads_out,
+                                                 grad_scatter=self.bucket.scatter_descriptor(), live_count=self.live)
                                 for cam in self.pseudo_cameras]
         self.pair_graphs = {}
 
@@ -191,7 +225,7 @@ class GaussianTrainer:
         return S(image_height=cam.height, image_width=cam.width, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=self.bg,
                  scale_modifier=1.0, viewmatrix=t(cam.viewmatrix), projmatrix=t(cam.projmatrix), sh_degree=self.active_sh_degree,
                  campos=t(cam.campos), prefiltered=False, debug=False, include_feature=True,
-                 confidence=torch.ones((self.P, 1), device=self.dev))
+                 confidence=torch.ones((self.Pcap, 1), device=self.dev))
 
     def oneup_sh_degree(self):
         """GaussianModel.oneupSHdegree (scene/gaussian_model.py:182-184): one more SH band takes part in rendering and
@@ -200,8 +234,9 @@ class GaussianTrainer:
         if self.active_sh_degree >= self.sh_degree:
             return self.active_sh_degree
         self.active_sh_degree += 1
-        for s in self.sessions:
+        for s in list(self.sessions) + list(self.pseudo_sessions):
             s.v.sh_degree = self.active_sh_degree
+        self.pair_graphs = {}
         if self.graphs is not None:
             self.capture()
         return self.active_sh_degree
@@ -239,12 +274,12 @@ class GaussianTrainer:
 
     def _param_state(self, view):
         ps = ParamState()
-        ps.P = self.P
+        ps.P = self.Pcap  # spare rows are inert: zero gradients and zero moments leave them where they are
         seg = dict(xyz="xyz", shs="shs", opacity="opacity", scaling="scaling", rotation="rotation", feature="language_feature")
         for k in self.widths:
-            setattr(ps, k, self.raw[k].data_ptr())
-            setattr(ps, "m_" + k, self.m[k].data_ptr())
-            setattr(ps, "v_" + k, self.v[k].data_ptr())
+            setattr(ps, k, self._cap["raw"][k].data_ptr())
+            setattr(ps, "m_" + k, self._cap["m"][k].data_ptr())
+            setattr(ps, "v_" + k, self._cap["v"][k].data_ptr())
             setattr(ps, "g_" + k, self.bucket.segment(seg[k]).data_ptr())
         ps.opacity_act, ps.scaling_act, ps.rotation_act = (self.act["opacity"].data_ptr(), self.act["scaling"].data_ptr(),
                                                            self.act["rotation"].data_ptr())
@@ -398,7 +433,10 @@ class GaussianTrainer:
         draws from `generator` (or the global CUDA generator) -- seed it identically on every rank.
         proximity() (scene/gaussian_model.py:513-533, run while iteration < 2000): isolated, large Gaussians grow three
         new ones half-way to their nearest neighbours; the kNN the reference takes from its un-vendored simple_knn fork is
-        b200gs_knn3 here.  Buffers are re-allocated and, with `recapture`, the per-view graphs are captured again."""
+        b200gs_knn3 here.  The per-Gaussian buffers are capacity-sized: as long as the new count fits (and the binning
+        workspaces still cover the expected instance count) the rows are rewritten in place and the count is published through
+        the device word the kernels read, so nothing is re-allocated and no CUDA graph is captured again; otherwise the buffers
+        are rebuilt with head-room and, with `recapture`, the graphs captured again."""
         import time
         iteration = self.iteration if iteration is None else iteration
         if parallel.world()[1] > 1:
@@ -410,7 +448,7 @@ class GaussianTrainer:
         raw = {k: t.clone() for k, t in self.raw.items()}
         m = {k: t.clone() for k, t in self.m.items()}
         v = {k: t.clone() for k, t in self.v.items()}
-        accum, denom = self.bucket.segment("xyz_gradient_accum").clone(), self.bucket.segment("denom").clone()
+        accum, denom = self._stat("xyz_gradient_accum").clone(), self._stat("denom").clone()
         grads = accum / denom
         grads[grads.isnan()] = 0.0
         get_scaling = lambda: torch.exp(raw["scaling"])
@@ -465,17 +503,27 @@ class GaussianTrainer:
             mask = torch.logical_or(torch.logical_or(mask, big_vs), big_ws)
         prune(mask)
         # the instance count grows with the Gaussian count: keep 1.3x the largest count seen, scaled by the growth
-        need = int(1.3 * self._max_rendered * max(1.0, raw["xyz"].shape[0] / max(P_before, 1))) + 4096
-        self.capacity = max(self.capacity, need)
+        P_new = int(raw["xyz"].shape[0])
+        need = int(1.3 * self._max_rendered * max(1.0, P_new / max(P_before, 1))) + 4096
         torch.cuda.synchronize(self.dev); t_logic = time.perf_counter()
-        self._allocate(raw, m, v)
+        in_place = P_new <= self.Pcap and need <= self.capacity
+        if in_place:
+            # the buffers have room: new rows are written where they are, the spare rows made inert, the count published in the
+            # device word the kernels read -- every session, workspace and captured graph stays as it is
+            self._write_rows(raw, m, v, P_before)
+            self.bucket.zero_()       # densification_postfix: statistics start again (the gradient segments are rewritten every step)
+            self.g_means2D.zero_()
+        else:
+            self.capacity = max(self.capacity, need)
+            self._allocate(raw, m, v, rows=P_new + P_new // 4 + 1024)  # head-room: the next events work in place
         self._refresh_activations()
         torch.cuda.synchronize(self.dev); t_alloc = time.perf_counter()
-        if recapture:
+        if recapture and not in_place:
             self.capture()
         torch.cuda.synchronize(self.dev); t_end = time.perf_counter()
-        tm = self.densify_timing = getattr(self, "densify_timing", dict(events=0, logic_s=0.0, allocate_s=0.0, capture_s=0.0))
-        tm["events"] += 1; tm["logic_s"] += t_logic - t_start; tm["allocate_s"] += t_alloc - t_logic; tm["capture_s"] += t_end - t_alloc
+        tm = self.densify_timing = getattr(self, "densify_timing", dict(events=0, in_place=0, logic_s=0.0, allocate_s=0.0, capture_s=0.0))
+        tm["events"] += 1; tm["in_place"] += int(in_place)
+        tm["logic_s"] += t_logic - t_start; tm["allocate_s"] += t_alloc - t_logic; tm["capture_s"] += t_end - t_alloc
         return self.P
 
     def reset_opacity(self):
@@ -492,8 +540,8 @@ class GaussianTrainer:
         c = lambda t: t.detach().cpu().clone()
         return dict(iteration=self.iteration, hparams=dict(self.hp), raw={k: c(v) for k, v in self.raw.items()},
                     exp_avg={k: c(v) for k, v in self.m.items()}, exp_avg_sq={k: c(v) for k, v in self.v.items()},
-                    xyz_gradient_accum=c(self.bucket.segment("xyz_gradient_accum")), denom=c(self.bucket.segment("denom")),
-                    max_radii2D=c(self.bucket.max_radii2D))
+                    xyz_gradient_accum=c(self._stat("xyz_gradient_accum")), denom=c(self._stat("denom")),
+                    max_radii2D=c(self._stat("max_radii2D")))
 
     def restore(self, state, recapture=True):
         """Inverse of capture_state (GaussianModel.restore, scene/gaussian_model.py:104-143)."""
@@ -501,9 +549,9 @@ class GaussianTrainer:
         self.hp.update(state.get("hparams", {}))
         self._allocate({k: to(v) for k, v in state["raw"].items()}, {k: to(v) for k, v in state["exp_avg"].items()},
                        {k: to(v) for k, v in state["exp_avg_sq"].items()})
-        self.bucket.segment("xyz_gradient_accum").copy_(to(state["xyz_gradient_accum"]))
-        self.bucket.segment("denom").copy_(to(state["denom"]))
-        self.bucket.max_radii2D.copy_(state["max_radii2D"].to(self.dev))
+        self._stat("xyz_gradient_accum").copy_(to(state["xyz_gradient_accum"]))
+        self._stat("denom").copy_(to(state["denom"]))
+        self._stat("max_radii2D").copy_(state["max_radii2D"].to(self.dev))
         self.iteration = int(state["iteration"])
         self.set_hparams(step=self.iteration + 1)
         self._refresh_activations()
@@ -543,8 +591,8 @@ class GaussianTrainer:
             opt.state[p] = {"step": torch.tensor(float(self.iteration)), "exp_avg": m[g["name"]].detach().clone().contiguous(),
                             "exp_avg_sq": v[g["name"]].detach().clone().contiguous()}
         return (self.active_sh_degree, leaves["xyz"], leaves["f_dc"], leaves["f_rest"], torch.empty(0), leaves["scaling"], leaves["rotation"],
-                leaves["opacity"], leaves["language_feature"], self.bucket.max_radii2D.detach().clone().float(),
-                self.bucket.segment("xyz_gradient_accum").detach().clone(), self.bucket.segment("denom").detach().clone(),
+                leaves["opacity"], leaves["language_feature"], self._stat("max_radii2D").detach().clone().float(),
+                self._stat("xyz_gradient_accum").detach().clone(), self._stat("denom").detach().clone(),
                 opt.state_dict(), float(hp["spatial_lr_scale"]), torch.ones((self.P, 1), device=self.dev))
 
     def restore_reference(self, model_args, recapture=True):
@@ -577,9 +625,9 @@ class GaussianTrainer:
         self.hp["spatial_lr_scale"] = float(spatial)
         self.active_sh_degree = int(deg)
         self._allocate(raw, m, v)
-        self.bucket.segment("xyz_gradient_accum").copy_(to(accum).reshape(P, 1))
-        self.bucket.segment("denom").copy_(to(denom).reshape(P, 1))
-        self.bucket.max_radii2D.copy_(max_radii2D.detach().to(self.dev).to(torch.int32))
+        self._stat("xyz_gradient_accum").copy_(to(accum).reshape(P, 1))
+        self._stat("denom").copy_(to(denom).reshape(P, 1))
+        self._stat("max_radii2D").copy_(max_radii2D.detach().to(self.dev).to(torch.int32))
         self.iteration = int(max(steps)) if steps else 0
         self.set_hparams(step=self.iteration + 1)
         self._refresh_activations()

@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(
 	int32_t* __restrict__ radii, float* __restrict__ depths, ushort4* __restrict__ rects, float4* __restrict__ rec,
 	uint8_t* __restrict__ clamped, uint32_t* __restrict__ sort_keys, uint32_t* __restrict__ sort_vals,
 	uint32_t* __restrict__ depth_hist /*[4][256]: digit histograms of all four depth-sort passes*/, uint2* __restrict__ ranges, uint32_t* __restrict__ tile_count, int count_stride, int tiles, GeomHeader* __restrict__ hdr,
-	int tma_ok)
+	int tma_ok, const uint32_t* live_count)
 {
 	// digit histograms of the depth-sort keys for all four radix passes that follow (taken here, where the key is
 	// produced: one conflict-bounded shared-memory atomic per digit per Gaussian; taking them inside the passes cost
@@ -224,6 +224,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(
 	const float pz = xform_row(v, 2, x, y, z);
 	bool alive = !(pz <= 0.2f);  // in_frustum, auxiliary.h:154
 	if (!alive && prefiltered) atomicOr(&hdr->prefilter_violation, 2u);  // reference: printf + __trap (auxiliary.h:156-160)
+	if (live_count != nullptr && (uint32_t)idx >= __ldcg(live_count)) alive = false;  // a spare row of a capacity-sized buffer (b200gs_gaussians_t.live_count)
 
 	if (alive) {
 		const float hx = xform_row(vc.proj, 0, x, y, z), hy = xform_row(vc.proj, 1, x, y, z);
@@ -800,7 +801,7 @@ void launch_preprocess_forward(const b200gs_view_t& v, const b200gs_gaussians_t&
 		g.cov3D_precomp, g.colors_precomp, g.language_feature_precomp, g.shs_language, g.confidence,
 		v.viewmatrix, v.projmatrix, v.campos, v.width, v.height, v.tan_fovx, v.tan_fovy, focal_x, focal_y,
 		v.extended, v.prefiltered, radii, gs.depths, gs.rect, gs.rec, gs.clamped, gs.key_a, gs.order, gs.hist, is.ranges, is.tile_count, tile_count_stride(),
-		((v.width + TILE_X - 1) / TILE_X) * ((v.height + TILE_Y - 1) / TILE_Y), gs.hdr, tma_ok);
+		((v.width + TILE_X - 1) / TILE_X) * ((v.height + TILE_Y - 1) / TILE_Y), gs.hdr, tma_ok, g.live_count);
 	count_launch();
 }
 

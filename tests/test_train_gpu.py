@@ -407,23 +407,32 @@ def test_knn3_and_proximity_densification():
 
 
 @gpu
-def test_densify_and_prune_matches_the_reference_procedure():
+@pytest.mark.parametrize("spare_rows", [False, True])
+def test_densify_and_prune_matches_the_reference_procedure(spare_rows):
     """GaussianTrainer.densify_and_prune against scene/gaussian_model.py:400-608 restated on nn.Parameters + the torch
     optimizer state (oracle/train_torch.py::DensifyModel): same statistics, same RNG seed -> identical rows, row order
-    and Adam moments (everything is copied or computed by the same torch ops)."""
+    and Adam moments (everything is copied or computed by the same torch ops).  spare_rows: the trainer's buffers have
+    room for the new count, so the event happens in place -- same rows, and no session, workspace or CUDA graph is rebuilt."""
     from b200gs.trainer import GaussianTrainer, DEFAULTS
     from oracle import train_torch as tt
     dev = torch.device("cuda", 0)
     sc, cams, gts, monos, raw = _trainer_inputs("small", dev)
-    tr = GaussianTrainer(cameras=cams, gt_images=gts, depth_mono=monos, device=dev, capacity=400_000, **raw)
+    P0 = int(raw["xyz"].shape[0])
+    tr = GaussianTrainer(cameras=cams, gt_images=gts, depth_mono=monos, device=dev, capacity=400_000,
+                         gaussian_capacity=2 * P0 if spare_rows else None, **raw)
     tr.capture()
+    graphs_before, sessions_before = tr.graphs, list(tr.sessions)
     for it in range(6):
         tr.step(it % len(cams))
     torch.cuda.synchronize()
     P = tr.P
+    assert P == P0 and tr.Pcap == (2 * P0 if spare_rows else P0)
+    if spare_rows:  # the spare rows are inert: culled, never updated
+        assert int(tr.sessions[0].radii[P:].abs().max()) == 0
+        assert float(tr._cap["raw"]["xyz"][P:].abs().max()) == 0.0 and float(tr._cap["m"]["shs"][P:].abs().max()) == 0.0
     snap = {k: v.clone() for k, v in tr.raw.items()}
     mom = {k: (tr.m[k].clone(), tr.v[k].clone()) for k in tr.raw}
-    accum, denom = tr.bucket.segment("xyz_gradient_accum").clone(), tr.bucket.segment("denom").clone()
+    accum, denom = tr._stat("xyz_gradient_accum").clone(), tr._stat("denom").clone()
     assert float(denom.sum()) > 0
     thr = float(torch.quantile((accum / denom.clamp_min(1)).squeeze(), 0.9))  # top 10 % densify
     extent = 3.0
@@ -453,11 +462,25 @@ def test_densify_and_prune_matches_the_reference_procedure():
     for k in tr.m:
         assert torch.equal(tr.m[k], m_ref[k]), k
     assert float(tr.bucket.segment("denom").sum()) == 0.0  # statistics reset
+    if spare_rows:
+        assert tr.densify_timing["in_place"] == 1 and tr.graphs is graphs_before and all(a is b for a, b in zip(tr.sessions, sessions_before))
+    else:
+        assert tr.densify_timing["in_place"] == 0 and tr.Pcap > newP  # rebuilt with head-room: the next event works in place
     # and training goes on with the new Gaussian count
     for it in range(3):
         tr.step(it % len(cams))
     torch.cuda.synchronize()
     assert np.isfinite(tr.loss_values()[0])
+    assert int(tr.sessions[0].radii[newP:].abs().max() if tr.Pcap > newP else 0) == 0
+    assert int((tr.sessions[0].radii[:newP] > 0).sum()) > 0
+    # a second event (prune-heavy: the count shrinks) is in place in both set-ups
+    g3 = torch.Generator(device=dev).manual_seed(99)
+    P2 = tr.densify_and_prune(iteration=3000, generator=g3, max_grad=1e9, min_opacity=0.3, extent=extent, max_screen_size=20)
+    assert P2 < newP and tr.densify_timing["in_place"] >= 1
+    for it in range(3):
+        tr.step(it % len(cams))
+    torch.cuda.synchronize()
+    assert np.isfinite(tr.loss_values()[0]) and int(tr.sessions[0].radii[P2:].abs().max()) == 0
     tr.reset_opacity()
     assert float(torch.sigmoid(tr.raw["opacity"]).max()) <= 0.01 + 1e-6
 

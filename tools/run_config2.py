@@ -148,7 +148,7 @@ def run_ours():
             w = min((it - START_PSEUDO) / 500.0, 1.0) * PSEUDO_W
             if w != w_set:
                 tr.set_pseudo_weight(w); w_set = w
-            tr.step_pair(v, pv, adam=not dens, use_graph=it >= DENSIFY_UNTIL)
+            tr.step_pair(v, pv, adam=not dens)  # (the pair graphs survive densification: the Gaussian count is a device word)
         elif dens:
             tr.step_stats_only(v)
         else:
@@ -170,8 +170,8 @@ def run_ours():
         for name, cams, ref in (("train", train_cams, gts), ("test", test_cams, test_gt)):
             for c, g in zip(cams, ref):
                 col = GaussianRasterizer(tr._default_settings(c))(means3D=tr.raw["xyz"], means2D=torch.zeros_like(tr.raw["xyz"]),
-                                                                 opacities=tr.act["opacity"], shs=tr.raw["shs"].view(tr.P, 16, 3),
-                                                                 scales=tr.act["scaling"], rotations=tr.act["rotation"],
+                                                                 opacities=tr.act["opacity"][:tr.P], shs=tr.raw["shs"].view(tr.P, 16, 3),
+                                                                 scales=tr.act["scaling"][:tr.P], rotations=tr.act["rotation"][:tr.P],
                                                                  shs_language=tr.raw["feature"])[0]
                 out[name].append(psnr(col, g))
     return dict(iters_per_s=A.iters / sec, seconds=sec, final_P=tr.P, psnr_train=out["train"], psnr_test=out["test"],
