@@ -522,7 +522,8 @@ def run_b200gs(args, rank, world, local):
                 "blend_bwd": model["backward"]["blend_bwd"], "preprocess_bwd": model["backward"]["preprocess_bwd"]}
     # the reference's single 64-bit sort is split here into depth_sort + tile_sort: charge its bytes to their sum
     sort_ms = stage_ms["depth_sort"] + stage_ms["tile_sort"]
-    dom = max((k for k in by_stage if k not in ("depth_sort",)), key=lambda k: stage_ms[k] if k != "tile_sort" else sort_ms)
+    # the dominant KERNEL (one launch): each sort is a launch of its own, so they compete with their own times
+    dom = max((k for k in by_stage if k not in ("depth_sort",)), key=lambda k: stage_ms[k])
     dom_ms = sort_ms if dom == "tile_sort" else stage_ms[dom]
     achieved = by_stage[dom] / (dom_ms * 1e-3) / 1e9
     # DRAM traffic and warp-instruction count of the dominant kernel from the committed ncu capture -- only when that capture
@@ -540,7 +541,7 @@ def run_b200gs(args, rank, world, local):
                     # the ceiling that does bind the blend kernels: warp instructions issued / issue slots available in the kernel's time
                     issue = dict(warp_instructions=inst, slots_per_cycle=slots, sm_mhz=clocks["sm_mhz"],
                                  frac=inst / (slots * clocks["sm_mhz"] * 1e6 * dom_ms * 1e-3),
-                                 floor_us=inst / (slots * clocks["sm_mhz"]), source="smsp__inst_executed.sum, profiles/r02_blend_ncu_full_summary.csv")
+                                 floor_us=inst / (slots * clocks["sm_mhz"]), source="smsp__inst_executed.sum, " + tj.get("source", "profiles/"))
         except Exception:
             traffic, issue = None, None
     total_bytes = model["bytes_fwd"] + model["bytes_bwd"]
@@ -549,7 +550,8 @@ def run_b200gs(args, rank, world, local):
                     step=dict(algorithmic_bytes=total_bytes, achieved=total_bytes / (ms_per_step * 1e-3) / 1e9,
                               frac=total_bytes / (ms_per_step * 1e-3) / 1e9 / peak),
                     stage_ms=stage_ms, stage_sum_ms=sum(stage_ms.values()),
-                    note="the blend kernels are issue-slot bound (FP32 pair evaluation), not HBM bound: `issue.frac` is the fraction that describes them; see DESIGN.md")
+                    note="the blend kernels are not HBM bound (their working set is L2 resident): FP32 pair evaluation, with the kernel's duration set by its "
+                         "deepest units (one warp each) at this image size; `issue.frac` = warp instructions / issue slots in the kernel's time; see DESIGN.md")
 
     train = None
     if not args.fwd_only and ext and not args.no_train:

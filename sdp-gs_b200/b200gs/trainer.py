@@ -502,9 +502,9 @@ class GaussianTrainer:
             big_ws = get_scaling().max(dim=1).values > 0.1 * extent
             mask = torch.logical_or(torch.logical_or(mask, big_vs), big_ws)
         prune(mask)
-        # the instance count grows with the Gaussian count: keep 1.3x the largest count seen, scaled by the growth
+        # the instance count grows with the Gaussian count: expect the largest count seen so far, scaled by the growth, plus 15 %
         P_new = int(raw["xyz"].shape[0])
-        need = int(1.3 * self._max_rendered * max(1.0, P_new / max(P_before, 1))) + 4096
+        need = int(1.15 * self._max_rendered * max(1.0, P_new / max(P_before, 1))) + 4096
         torch.cuda.synchronize(self.dev); t_logic = time.perf_counter()
         in_place = P_new <= self.Pcap and need <= self.capacity
         if in_place:
@@ -514,8 +514,8 @@ class GaussianTrainer:
             self.bucket.zero_()       # densification_postfix: statistics start again (the gradient segments are rewritten every step)
             self.g_means2D.zero_()
         else:
-            self.capacity = max(self.capacity, need)
-            self._allocate(raw, m, v, rows=P_new + P_new // 4 + 1024)  # head-room: the next events work in place
+            self.capacity = max(self.capacity, need + need // 2)       # head-room in the binning workspaces and ...
+            self._allocate(raw, m, v, rows=P_new + P_new // 4 + 1024)  # ... in the rows: the next events work in place
         self._refresh_activations()
         torch.cuda.synchronize(self.dev); t_alloc = time.perf_counter()
         if recapture and not in_place:
