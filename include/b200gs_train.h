@@ -60,7 +60,13 @@ typedef struct b200gs_param_state {
 
 /* One fused launch: chain rule through the activations, Adam update, re-activation, densification statistics.
  * `update` == 0 only refreshes the activated copies from the raw parameters (no gradient needed); 2 = densification
- * statistics only (train.py:218-231 on a densify iteration: the parameters were just re-created, optimizer.step() is a no-op). */
+ * statistics only (train.py:218-231 on a densify iteration: the parameters were just re-created, optimizer.step() is a no-op).
+ * Add B200GS_STEP_AFTER_FOREIGN (4) when the previous operation in the stream is NOT one of this library's kernels (an NCCL
+ * all-reduce, a copy, a torch kernel): the launch then uses full stream ordering instead of a programmatic dependent launch. */
+#define B200GS_STEP_AFTER_FOREIGN 4
+/* sizeof(b200gs_param_state_t), sizeof(b200gs_hparams_t): checked by bindings at load time */
+void b200gs_train_abi_sizes(int64_t* out2);
+
 int b200gs_param_step(const b200gs_param_state_t* s, const b200gs_hparams_t* hp_device, int32_t update, void* stream);
 
 /* End of an iteration: step += 1 and lr_xyz = the exponential position schedule of utils/general_utils.py:
@@ -71,7 +77,8 @@ int b200gs_param_step(const b200gs_param_state_t* s, const b200gs_hparams_t* hp_
 int b200gs_hparams_advance(b200gs_hparams_t* hp_device, float lr_init, float lr_final, float lr_delay_mult,
                            float max_steps, void* stream);
 
-/* loss_out (device f64[4]): [0] += (1-l)*L1 + l*(1-SSIM), [1] L1, [2] SSIM (both means), written by the last block.
+/* loss_out (device f64[4]): [0] = (1-l)*L1 + l*(1-SSIM) (assigned: the depth losses add to it afterwards), [1] L1, [2] SSIM
+ * (both means), written by the last block.
  * scratch: device f32[3*3*H*W] (the three derivative maps).  dL_dimage: device f32[3,H,W], fully written.
  * accum: device f64[b200gs_loss_accum_doubles()], must be zero on entry (the kernel leaves it zero on exit); partial
  * sums are spread over 64 lines so that the per-block atomics do not serialise in L2. */

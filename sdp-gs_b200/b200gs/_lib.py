@@ -80,7 +80,7 @@ class ParamState(C.Structure):  # b200gs_param_state_t
 
 
 TRAIN_EXPORTS = ["b200gs_param_step", "b200gs_photometric_loss", "b200gs_photometric_scratch_bytes",
-                 "b200gs_depth_pearson_loss", "b200gs_hparams_advance", "b200gs_loss_accum_doubles", "b200gs_knn3", "b200gs_depth_pearson_loss_pseudo"]
+                 "b200gs_depth_pearson_loss", "b200gs_hparams_advance", "b200gs_loss_accum_doubles", "b200gs_knn3", "b200gs_depth_pearson_loss_pseudo", "b200gs_train_abi_sizes"]
 COLLECTIVE_EXPORTS = ["b200gs_allreduce_sum_f32", "b200gs_allreduce_flag_words", "b200gs_gather_reduce_f32"]
 
 EXPORTS = [
@@ -146,6 +146,11 @@ def _load():
     mine = [C.sizeof(t) for t in (View, Gaussians, Outputs, Workspace, GradOutputs, Grads)]
     if list(sizes) != mine:
         raise ImportError(f"ABI mismatch between {LIB_PATH} {list(sizes)} and this binding {mine}")
+    tsizes = (C.c_int64 * 2)()
+    lib.b200gs_train_abi_sizes.argtypes = [P(C.c_int64)]
+    lib.b200gs_train_abi_sizes(tsizes)
+    if list(tsizes) != [C.sizeof(ParamState), C.sizeof(HParams)]:
+        raise ImportError(f"ABI mismatch (training structs) between {LIB_PATH} {list(tsizes)} and this binding")
     return lib
 
 

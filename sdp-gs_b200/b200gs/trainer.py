@@ -323,7 +323,9 @@ class GaussianTrainer:
 
     def _back(self, view):
         ps = self._param_state(view)
-        check(lib.b200gs_param_step(C.byref(ps), self.hp_dev.data_ptr(), 1, rz._stream()))
+        # behind an NCCL all-reduce the previous kernel in the stream is not ours: full stream ordering (B200GS_STEP_AFTER_FOREIGN)
+        foreign = 4 if (parallel.world()[1] > 1 and not self.bucket.fused_exchange and self.bucket._symm is None) else 0
+        check(lib.b200gs_param_step(C.byref(ps), self.hp_dev.data_ptr(), 1 | foreign, rz._stream()))
         li, lf, dm, ms = self._xyz_schedule()
         check(lib.b200gs_hparams_advance(self.hp_dev.data_ptr(), li, lf, dm, ms, rz._stream()))
 

@@ -516,7 +516,11 @@ int b200gs_hparams_advance(b200gs_hparams_t* hp, float lr_init, float lr_final, 
 	return 0;
 }
 
+void b200gs_train_abi_sizes(int64_t* out2) { out2[0] = sizeof(b200gs_param_state_t); out2[1] = sizeof(b200gs_hparams_t); }
+
 int b200gs_param_step(const b200gs_param_state_t* s, const b200gs_hparams_t* hp, int32_t update, void* stream_) {
+	const bool foreign = (update & B200GS_STEP_AFTER_FOREIGN) != 0;
+	update &= 3;
 	if (!s || !hp || s->P < 0) return train_fail(B200GS_E_ARG, "param_step: bad arguments");
 	if (s->P == 0) return 0;
 	if (!s->xyz || !s->shs || !s->opacity || !s->scaling || !s->rotation || !s->opacity_act || !s->scaling_act || !s->rotation_act)
@@ -528,8 +532,9 @@ int b200gs_param_step(const b200gs_param_state_t* s, const b200gs_hparams_t* hp,
 	if (update && s->xyz_gradient_accum && (!s->denom || !s->max_radii2D || !s->g_means2D || !s->radii))
 		return train_fail(B200GS_E_ARG, "param_step: densification statistics need denom, max_radii2D, g_means2D and radii");
 	cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-	// its predecessor is the preprocess backward (ours) in a training step; launched plainly when used stand-alone
-	launch_k(update ? PDL_TRAIN : 0u, param_step_kernel, dim3(148 * 8), dim3(256), stream, *s, hp, (int)update);
+	// its predecessor is the preprocess backward or the gather kernel (ours: both execute griddepcontrol.wait) in a training step;
+	// launched with full stream ordering when used stand-alone or behind a foreign kernel (B200GS_STEP_AFTER_FOREIGN)
+	launch_k((update && !foreign) ? PDL_TRAIN : 0u, param_step_kernel, dim3(148 * 8), dim3(256), stream, *s, hp, (int)update);
 	count_launch();
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return train_fail(B200GS_E_CUDA, cudaGetErrorString(e));
