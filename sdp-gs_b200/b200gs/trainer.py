@@ -56,6 +56,12 @@ class GaussianTrainer:
         self.nacc = int(lib.b200gs_loss_accum_doubles())
         self.accum = torch.zeros((2 * self.nacc,), dtype=torch.float64, device=dev)  # photometric | depth
         self.loss = torch.zeros((4,), dtype=torch.float64, device=dev)
+        # The depth loss of the training view runs on a second stream beside the photometric loss (both only read the render; in a
+        # captured iteration they become two branches of the graph).  It reports into its own block so that the two kernels
+        # never touch the same word: [3] is the weighted depth loss, [0] is unused; loss_values() adds the two.
+        self.loss_depth = torch.zeros((4,), dtype=torch.float64, device=dev)
+        self._side = torch.cuda.Stream(device=dev)
+        self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
         self.scratch = torch.empty((lib.b200gs_photometric_scratch_bytes(W, H) // 4,), dtype=torch.float32, device=dev)
         self.iteration = 0
         self.capacity = capacity
@@ -305,11 +311,17 @@ class GaussianTrainer:
             s.gr.scatter_bases = self._scatter[0] if push else None
         s.forward()
         st = rz._stream()
+        main = torch.cuda.current_stream(self.dev)
+        self._ev_fork.record(main)
+        self._side.wait_event(self._ev_fork)
+        check(lib.b200gs_depth_pearson_loss(s.depth.data_ptr(), self.mono[view].data_ptr(), self.W * self.H, self.hp_dev.data_ptr(),
+                                            self.accum[self.nacc:].data_ptr(), self.loss_depth.data_ptr(), s.cot["depth"].data_ptr(),
+                                            C.c_void_p(self._side.cuda_stream)))
+        self._ev_join.record(self._side)
         check(lib.b200gs_photometric_loss(s.color.data_ptr(), self.gt[view].data_ptr(), self.W, self.H, self.hp_dev.data_ptr(),
                                           self.scratch.data_ptr(), self.accum.data_ptr(), self.loss.data_ptr(),
                                           s.cot["color"].data_ptr(), st))
-        check(lib.b200gs_depth_pearson_loss(s.depth.data_ptr(), self.mono[view].data_ptr(), self.W * self.H, self.hp_dev.data_ptr(),
-                                            self.accum[self.nacc:].data_ptr(), self.loss.data_ptr(), s.cot["depth"].data_ptr(), st))
+        main.wait_event(self._ev_join)
         s.backward()
 
     def _exchange(self):
@@ -646,8 +658,10 @@ class GaussianTrainer:
     def loss_values(self):
         """(total, L1, SSIM, weighted depth loss) of the last step.  Synchronizes, and checks the binning capacity."""
         t = self.loss.cpu().numpy()
+        d = self.loss_depth.cpu().numpy()
         self.check_overflow()
-        return float(t[0]), float(t[1]), float(t[2]), float(t[3])
+        # loss[0] = photometric (+ the pseudo view's depth term, which adds itself), loss_depth[3] = the training view's depth term
+        return float(t[0] + d[3]), float(t[1]), float(t[2]), float(d[3])
 
     def parameters(self):
         return {k: v for k, v in self.raw.items()}
