@@ -6,17 +6,22 @@
 // fma(q, -0.5, -(dy*(dx*b))), CUDA expf, fma(T, alpha*c, C)), so the image is bit-identical; the decomposition
 // is not the reference's:
 //   * unit of work = one warp = one 8x4 pixel block of a 16x16 tile.  Warps are autonomous (no CTA barrier
-//     anywhere): a persistent grid of 4-warp CTAs draws units from a global ticket, longest tile list first
-//     (order built by the binning stage), fewer warps than units, so SMs that drew light units keep drawing;
+//     anywhere): a persistent grid of 4-warp CTAs draws units from a global ticket, heaviest tile first -- by
+//     what the tile's units cost the last time the workspace rendered (ImageState::tile_cost, persistent
+//     workspaces; the kernels record 4 x rounds + survivors per unit), else by list length;
 //   * a round = 32 consecutive entries of the tile's sorted list, one per lane.  Ids are loaded three rounds
 //     ahead, the 32-byte geometry half of the splat record two rounds ahead (registers), the lane then runs the
 //     conservative ellipse-vs-block cull (blend_common.cuh) and only survivors (39 % on the LLFF shape) are
 //     appended, in list order, to a 64-slot ring in the warp's shared memory; their payload half (colour, depth,
 //     feature) is fetched by cp.async straight into the ring, up to K_INFLIGHT rounds of copies in flight;
 //   * per-pixel work runs on dense, 16-aligned batches of survivors read from shared memory as broadcasts with
-//     immediate offsets; the loops carry no index arithmetic, bounds checks or per-survivor bookkeeping loads
-//     (ncu, round 2: the kernels are issue bound -- 76 % / 65 % issue-slot utilisation -- on exactly these loops;
-//     trimming them from 71 / 125 to ~50 / ~85 warp instructions per survivor is what moved the time);
+//     immediate offsets, the pair evaluation on packed f32x2 instructions (two survivors per FADD2/FMUL2/FFMA2,
+//     blend_common.cuh); the loops carry no index arithmetic, bounds checks or per-survivor bookkeeping loads;
+//   * at the LLFF / DTU image sizes a kernel lasts as long as its deepest unit, and a unit is one warp running a
+//     chain of dependent FP32 operations (tools/blend_trace.py): the WIDE instantiations
+//     put more independent work in front of every serial stretch (all 16 alphas of a batch before its recurrence /
+//     the T-independent half of the backward's phase 1 for 8 survivors at a time) at 150-166 registers and 3 CTAs
+//     per SM; with many units per warp slot (1297x840 and up) the narrow instantiations at 6 / 5 CTAs per SM win;
 //   * backward: phase 1 (lane = pixel) replays the recurrence back to front and leaves two weights per
 //     (pixel, Gaussian) pair in shared memory; phase 2 (lane = (half, Gaussian)) turns them into the 13
 //     per-Gaussian sums -- six pixel moments of wg = G*dL/dG (-> dL/dmean2D, dL/dconic, dL/dopacity) on the
