@@ -17,6 +17,3 @@ timeout 300 $CMD > gpurun_out/r02b_ncu_plain.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/r02b_final_launches_raw.csv $CMD > gpurun_out/r02b_ncu_launches.log 2>&1
 tail -2 gpurun_out/r02b_ncu_launches.log
 grep -c libb200gs gpurun_out/r02b_final_bench_reference_n1.err
-CMD2="python tools/stage_times.py --no-graph --steps 3"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"blend_" -s 6 -c 2 -o gpurun_out/r02b_blend -f $CMD2 > gpurun_out/r02b_ncu_blend.log 2>&1
-tail -1 gpurun_out/r02b_ncu_blend.log
