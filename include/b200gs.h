@@ -101,8 +101,10 @@ typedef struct b200gs_workspace {
 	/* persistent != 0: the caller keeps these workspaces (and b200gs_grads_t.scratch) alive across calls, initialised them
 	 * once with b200gs_workspace_init, and lets nothing else write to them.  The kernels then leave every counter,
 	 * histogram and look-back word they consumed zeroed for the next call (and the backward re-zeroes the scratch rows it
-	 * read), so no call issues a memset -- the steady state of a training loop (CUDA-graph sessions).  0: fresh or foreign
-	 * memory; every call zeroes what it needs first (the eager autograd path, which allocates per call). */
+	 * read), so no call issues a memset -- the steady state of a training loop (CUDA-graph sessions).  A persistent image
+	 * workspace also carries, per tile, what its blend units cost in the previous call; the next call launches the units
+	 * heaviest first by that measure (scheduling only: results do not depend on it).  0: fresh or foreign memory; every call
+	 * zeroes what it needs first (the eager autograd path, which allocates per call) and orders the units by list length. */
 	int32_t persistent;
 	int32_t reserved_;
 } b200gs_workspace_t;
@@ -159,7 +161,7 @@ size_t b200gs_binning_bytes(int64_t capacity, int32_t width, int32_t height); /*
 size_t b200gs_scratch_bytes(int32_t P);
 
 /* One-time initialisation of persistent workspaces (see b200gs_workspace_t.persistent): zeroes the geom workspace's
- * counter region and, when `scratch` != NULL, the P*64-byte backward scratch. */
+ * counter region, the image workspace (no cost history yet) and, when `scratch` != NULL, the P*64-byte backward scratch. */
 int b200gs_workspace_init(const b200gs_workspace_t* ws, int32_t P, void* scratch, void* stream);
 
 /* Stage 1 of the forward: preprocess, depth ordering, instance count.  Needs ws->geom and

@@ -86,7 +86,9 @@ struct BinningState {
 
 // Radix sort tiling: 256 threads x ITEMS items per CTA tile.
 #define SORT_THREADS 256
+#ifndef SORT_ITEMS_SMALL
 #define SORT_ITEMS_SMALL 4
+#endif
 #define SORT_ITEMS_LARGE 16
 static inline int sort_items_for(int64_t n) { return n <= (1 << 20) ? SORT_ITEMS_SMALL : SORT_ITEMS_LARGE; }
 static inline int64_t sort_tiles_for(int64_t n) {
