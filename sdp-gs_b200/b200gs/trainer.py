@@ -459,63 +459,80 @@ class GaussianTrainer:
         t_start = time.perf_counter()
         self.check_overflow()
         P_before = self.P
-        raw = {k: t.clone() for k, t in self.raw.items()}
-        m = {k: t.clone() for k, t in self.m.items()}
-        v = {k: t.clone() for k, t in self.v.items()}
+        # The row logic works on three packed matrices [rows, 62] (parameters, first and second Adam moments; columns in the order
+        # of self.widths) instead of 18 per-group tensors, and on row indices taken once per mask: the same gathers and
+        # concatenations the reference performs per tensor (same rows, same order, same torch.normal draws), in a third of the
+        # torch calls and with one host read per mask instead of one per indexed tensor.
+        off, c = {}, 0
+        for k, w in self.widths.items():
+            off[k] = (c, c + w); c += w
+        R = torch.cat([self.raw[k] for k in self.widths], dim=1)
+        M = torch.cat([self.m[k] for k in self.widths], dim=1)
+        V = torch.cat([self.v[k] for k in self.widths], dim=1)
+        col = lambda T, k: T[:, off[k][0]:off[k][1]]
         accum, denom = self._stat("xyz_gradient_accum").clone(), self._stat("denom").clone()
         grads = accum / denom
-        grads[grads.isnan()] = 0.0
-        get_scaling = lambda: torch.exp(raw["scaling"])
+        grads = torch.where(grads.isnan(), torch.zeros_like(grads), grads)  # grads[grads.isnan()] = 0.0 without the host read
+        get_scaling = lambda: torch.exp(col(R, "scaling"))
+        rows_of = lambda mask: mask.nonzero().squeeze(1)
 
-        def cat(new):  # cat_tensors_to_optimizer + densification_postfix
-            for k in raw:
-                raw[k] = torch.cat((raw[k], new[k]), dim=0)
-                m[k] = torch.cat((m[k], torch.zeros_like(new[k])), dim=0)
-                v[k] = torch.cat((v[k], torch.zeros_like(new[k])), dim=0)
+        def cat(newR):  # cat_tensors_to_optimizer + densification_postfix: new rows start with zero moments
+            nonlocal R, M, V
+            z = torch.zeros_like(newR)
+            R, M, V = torch.cat((R, newR), dim=0), torch.cat((M, z), dim=0), torch.cat((V, z), dim=0)
 
         def prune(mask):  # prune_points: keep ~mask
+            nonlocal R, M, V
             if iteration > prune_from_iter:
-                keep = ~mask
-                for k in raw:
-                    raw[k], m[k], v[k] = raw[k][keep], m[k][keep], v[k][keep]
+                keep = rows_of(~mask)
+                R, M, V = R.index_select(0, keep), M.index_select(0, keep), V.index_select(0, keep)
 
         # densify_and_clone
         sel = torch.where(torch.norm(grads, dim=-1) >= max_grad, True, False)
         sel = torch.logical_and(sel, torch.max(get_scaling(), dim=1).values <= percent_dense * extent)
-        cat({k: t[sel] for k, t in raw.items()})
+        cat(R.index_select(0, rows_of(sel)))
         # densify_and_split
-        n_init = raw["xyz"].shape[0]
+        n_init = R.shape[0]
         padded = torch.zeros((n_init,), device=self.dev)
         padded[:grads.shape[0]] = grads.squeeze()
         sel = torch.where(padded >= max_grad, True, False)
         sel = torch.logical_and(sel, torch.max(get_scaling(), dim=1).values > percent_dense * extent)
-        stds = get_scaling()[sel].repeat(N, 1)
+        idx = rows_of(sel)
+        parents = R.index_select(0, idx)
+        scal = torch.exp(col(parents, "scaling"))
+        stds = scal.repeat(N, 1)
         means = torch.zeros((stds.size(0), 3), device=self.dev)
         samples = torch.normal(mean=means, std=stds, generator=generator)
-        rots = self._build_rotation(raw["rotation"][sel]).repeat(N, 1, 1)
-        new = {k: t[sel].repeat(N, 1) for k, t in raw.items()}
-        new["xyz"] = torch.bmm(rots, samples.unsqueeze(-1)).squeeze(-1) + raw["xyz"][sel].repeat(N, 1)
-        new["scaling"] = torch.log(get_scaling()[sel].repeat(N, 1) / (0.8 * N))
-        cat(new)
-        prune(torch.cat((sel, torch.zeros(N * int(sel.sum()), device=self.dev, dtype=bool))))
+        rots = self._build_rotation(col(parents, "rotation")).repeat(N, 1, 1)
+        newR = parents.repeat(N, 1)
+        col(newR, "xyz").copy_(torch.bmm(rots, samples.unsqueeze(-1)).squeeze(-1) + col(parents, "xyz").repeat(N, 1))
+        col(newR, "scaling").copy_(torch.log(scal.repeat(N, 1) / (0.8 * N)))
+        cat(newR)
+        prune(torch.cat((sel, torch.zeros(N * int(idx.numel()), device=self.dev, dtype=bool))))
         # proximity
-        if iteration < proximity_until_iter and raw["xyz"].shape[0] >= 4:
-            dist, nn = self.knn3(raw["xyz"])
+        if iteration < proximity_until_iter and R.shape[0] >= 4:
+            dist, nn = self.knn3(col(R, "xyz"))
             sel = torch.logical_and(dist > 5.0 * extent, torch.max(get_scaling(), dim=1).values > extent)
-            if bool(sel.any()):
-                idx = nn[sel].reshape(-1).long()
-                source = raw["xyz"][sel].repeat(1, 3, 1).reshape(-1, 3)  # the reference's own pairing (sources tiled, targets grouped)
-                rot = torch.zeros_like(raw["rotation"][idx])
-                rot[:, 0] = 1
-                cat(dict(xyz=(source + raw["xyz"][idx]) / 2, shs=torch.zeros_like(raw["shs"][idx]), opacity=raw["opacity"][idx],
-                         scaling=raw["scaling"][idx], rotation=rot, feature=raw["feature"][idx]))
+            src = rows_of(sel)
+            if int(src.numel()) > 0:
+                idx = nn.index_select(0, src).reshape(-1).long()
+                source = col(R, "xyz").index_select(0, src).repeat(1, 3, 1).reshape(-1, 3)  # the reference's own pairing (sources tiled, targets grouped)
+                newR = R.index_select(0, idx)  # opacity, scaling and feature of the neighbour
+                col(newR, "xyz").copy_((source + col(newR, "xyz")) / 2)
+                col(newR, "shs").zero_()
+                col(newR, "rotation").zero_()
+                newR[:, off["rotation"][0]] = 1
+                cat(newR)
         # prune (max_radii2D was reset by densification_postfix, so the screen-size test sees zeros, as in the reference)
-        mask = (torch.sigmoid(raw["opacity"]) < min_opacity).squeeze()
+        mask = (torch.sigmoid(col(R, "opacity")) < min_opacity).squeeze(1)
         if max_screen_size:
-            big_vs = torch.zeros((raw["xyz"].shape[0],), device=self.dev) > max_screen_size
+            big_vs = torch.zeros((R.shape[0],), device=self.dev) > max_screen_size
             big_ws = get_scaling().max(dim=1).values > 0.1 * extent
             mask = torch.logical_or(torch.logical_or(mask, big_vs), big_ws)
         prune(mask)
+        raw = {k: col(R, k) for k in self.widths}
+        m = {k: col(M, k) for k in self.widths}
+        v = {k: col(V, k) for k in self.widths}
         # the instance count grows with the Gaussian count: expect the largest count seen so far, scaled by the growth, plus 15 %
         P_new = int(raw["xyz"].shape[0])
         need = int(1.15 * self._max_rendered * max(1.0, P_new / max(P_before, 1))) + 4096
