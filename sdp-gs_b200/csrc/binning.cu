@@ -271,7 +271,6 @@ __global__ void __launch_bounds__(SORT_THREADS, ITEMS == SORT_ITEMS_LARGE ? 3 : 
 // look-back, and duplicateWithKeys (rasterizer_impl.cu:70-111) straight from the scanned offsets.  The depth
 // half of the reference's key is implied by the emission order, so only the tile id is written as sort key.
 // Also: digit histograms of the tile ids for the tile sort, and the zeroing of its look-back words.
-constexpr int EMIT_THREADS = SCAN_THREADS;
 constexpr int EMIT_ITEMS = SCAN_ITEMS;
 
 // TILE_COUNTS (images of at most COUNT_TILES_MAX tiles): every emitted instance is also counted into its tile, in
@@ -327,7 +326,9 @@ __device__ __forceinline__ void build_blend_orders(int tid, int nthreads, int ti
 	}
 }
 
-template <bool TILE_COUNTS>
+// EMIT_THREADS Gaussians per CTA: 1024, or 256 for small counts -- at 10 k Gaussians ten CTAs emitted 270 k instances in 40 us,
+// forty do it in half the time; at 100 k the shorter look-back chain of the 1024-thread CTAs wins.
+template <bool TILE_COUNTS, int EMIT_THREADS>
 __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(
 	const uint32_t* __restrict__ order, const ushort4* __restrict__ rect, int P, uint32_t grid_x, int64_t capacity,
 	int tile_bits, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ scan_state,
@@ -638,16 +639,18 @@ void launch_scan_emit(const b200gs_view_t& v, GeomState& gs, BinningState& bs, I
 	const int bit = (int)higher_msb(gx * gy);
 	const int64_t tiles_L = sort_tiles_for(capacity);
 	const int passes = (bit + 7) / 8;
-	const unsigned grid = (unsigned)((P + EMIT_THREADS * EMIT_ITEMS - 1) / (EMIT_THREADS * EMIT_ITEMS));
+	const int threads = scan_threads_for(P);
+	const unsigned grid = (unsigned)scan_tiles_for(P);
 	const int tiles = (int)(gx * gy);
-	if (tile_counts_path(tiles))
-		launch_impl(chained ? PDL_EMIT : 0u, scan_emit_kernel<true>, dim3(grid), dim3(EMIT_THREADS), stream, (const uint32_t*)gs.order, (const ushort4*)gs.rect, P, gx, capacity, bit,
+	uint32_t* cost = history ? is.tile_cost : (uint32_t*)nullptr;
+	auto go = [&](auto kernel) {
+		launch_impl(chained ? PDL_EMIT : 0u, kernel, dim3(grid), dim3(threads), stream, (const uint32_t*)gs.order, (const ushort4*)gs.rect, P, gx, capacity, bit,
 			bs.key_a, bs.val_a, reinterpret_cast<uint32_t*>(gs.scan_state), gs.hist + 4 * 256, bs.lookback, (size_t)passes * tiles_L * 256, gs.hdr,
-			is.tile_count, tiles, is.ranges, is.tile_order, is.tile_order_bwd, history ? is.tile_cost : (uint32_t*)nullptr);
-	else
-		launch_impl(chained ? PDL_EMIT : 0u, scan_emit_kernel<false>, dim3(grid), dim3(EMIT_THREADS), stream, (const uint32_t*)gs.order, (const ushort4*)gs.rect, P, gx, capacity, bit,
-			bs.key_a, bs.val_a, reinterpret_cast<uint32_t*>(gs.scan_state), gs.hist + 4 * 256, bs.lookback, (size_t)passes * tiles_L * 256, gs.hdr,
-			is.tile_count, tiles, is.ranges, is.tile_order, is.tile_order_bwd, history ? is.tile_cost : (uint32_t*)nullptr);
+			is.tile_count, tiles, is.ranges, is.tile_order, is.tile_order_bwd, cost);
+	};
+	const bool counts = tile_counts_path(tiles);
+	if (threads == SCAN_THREADS_SMALL) { if (counts) go(scan_emit_kernel<true, SCAN_THREADS_SMALL>); else go(scan_emit_kernel<false, SCAN_THREADS_SMALL>); }
+	else { if (counts) go(scan_emit_kernel<true, SCAN_THREADS>); else go(scan_emit_kernel<false, SCAN_THREADS>); }
 	count_launch();
 }
 

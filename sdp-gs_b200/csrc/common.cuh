@@ -95,9 +95,12 @@ static inline int64_t sort_tiles_for(int64_t n) {
 	int64_t per = (int64_t)SORT_THREADS * sort_items_for(n);
 	return (n + per - 1) / per;
 }
-#define SCAN_THREADS 1024
-#define SCAN_ITEMS 1  // Gaussians per thread in scan_emit_kernel (binning.cu: EMIT_THREADS x EMIT_ITEMS must match)
-static inline int64_t scan_tiles_for(int64_t n) { return (n + SCAN_THREADS * SCAN_ITEMS - 1) / (SCAN_THREADS * SCAN_ITEMS); }
+#define SCAN_THREADS 1024       // Gaussians per CTA of scan_emit_kernel (one per thread) ...
+#define SCAN_THREADS_SMALL 256  // ... and for small Gaussian counts (more CTAs to spread the emission over)
+#define SCAN_SMALL_MAX 32768
+#define SCAN_ITEMS 1
+static inline int scan_threads_for(int64_t n) { return n <= SCAN_SMALL_MAX ? SCAN_THREADS_SMALL : SCAN_THREADS; }
+static inline int64_t scan_tiles_for(int64_t n) { const int t = scan_threads_for(n); return (n + t - 1) / t; }
 
 GeomState geom_from_chunk(char* base, int P);
 ImageState image_from_chunk(char* base, int W, int H);
