@@ -188,24 +188,36 @@ def event_loop(K, warmup, step_fn, flush, world, after=None):
     return ms, wall
 
 
-def wall_loop(K, warmup, step_fn, world):
+E2E_REPEATS = 3
+E2E_BLOCKS = []  # ms per step of every block, one list per e2e measurement of this process (in call order)
+LAST_WALL = []  # seconds of every timed block of the last wall_loop call (reported next to the median)
+
+
+def wall_loop(K, warmup, step_fn, world, repeats=E2E_REPEATS):
+    """Host-clock timing of the end-to-end loops (both arms): `repeats` back-to-back blocks of exactly K steps, each bracketed by
+    a barrier + device synchronize; returns the MEDIAN block (the loop is host driven -- Python, the allocator, pinned copies --
+    and a single block occasionally catches a scheduling hiccup of tens of milliseconds; all blocks are reported)."""
     for i in range(warmup):
         step_fn(i)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(K):
-        step_fn(warmup + i)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    sec = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([sec], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        sec = float(t.item())
-    return sec
+    secs = []
+    for r in range(repeats):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(K):
+            step_fn(warmup + r * K + i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sec = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([sec], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        secs.append(sec)
+    LAST_WALL[:] = secs
+    return sorted(secs)[len(secs) // 2]
 
 
 # ------------------------------------------------------------------------------------------ our arm
@@ -258,6 +270,7 @@ def e2e_b200gs(args, wl, rank, world, dev):
         rz._check_pending(block=True)
     finally:
         rz.set_binning_capacity(None)
+    E2E_BLOCKS.append([1000.0 * x / args.steps for x in LAST_WALL])
     return world * args.steps / sec, sec, feeder.nbytes
 
 
@@ -507,7 +520,7 @@ def run_b200gs(args, rank, world, local):
         ve2e, vsec, vbytes = e2e_b200gs(args, wv, rank, world, dev)
         vanilla = dict(ms_per_view=vms / args.steps, views_per_s=1000.0 * args.steps / vms,
                        e2e=dict(value=ve2e, unit="views/s", ms_per_step=1000.0 * vsec / args.steps, h2d_bytes_per_step=vbytes,
-                                d2h_bytes_per_step=4 + 16))
+                                d2h_bytes_per_step=4 + 16, ms_per_step_blocks=E2E_BLOCKS[-1]))
 
     # ---- roofline of the dominant kernel + whole step
     L, V = int(np.mean(Ls)), int(np.mean(Vs))
@@ -592,7 +605,8 @@ def run_b200gs(args, rank, world, local):
                                 sort_passes_model=model["passes"], l2="flushed between steps (256 MiB write)",
                                 binning="capacity mode, CUDA graph replay", parallelism=f"image-parallel x{world}"),
                     e2e=dict(value=e2e_value, unit="views/s", ms_per_step=1000.0 * e2e_sec / args.steps,
-                             h2d_bytes_per_step=feeder_bytes, d2h_bytes_per_step=4 + 16,
+                             h2d_bytes_per_step=feeder_bytes, d2h_bytes_per_step=4 + 16, ms_per_step_blocks=E2E_BLOCKS[0],
+                             timing=f"median of {E2E_REPEATS} back-to-back blocks of exactly `steps` steps on the host clock, each bracketed by barrier + synchronize", 
                              path="diff_gaussian_rasterization.GaussianRasterizer + torch.autograd.backward (binning capacity 'auto'); "
                                   "every step's parameters are uploaded from pinned host memory (b200gs.hostio.PinnedFeeder: one copy per "
                                   "step on a copy stream, step i+1's upload overlapping step i's kernels); color.sum() copied back to pinned host "
@@ -892,9 +906,11 @@ def run_reference(args, rank, world, local):
         return float(rb.color.sum().item())
 
     e2e_sec = wall_loop(args.steps, max(3, args.warmup), step_e2e, 1)
+    e2e_blocks = [1000.0 * x / args.steps for x in LAST_WALL]
     if vanilla is not None:  # the like-for-like single-call comparison, end to end as well
         vsec = wall_loop(args.steps, max(3, args.warmup), lambda i: step_e2e(i, False), 1)
         vanilla["e2e"] = dict(value=args.steps / vsec, unit="views/s", ms_per_step=1000.0 * vsec / args.steps,
+                              ms_per_step_blocks=[1000.0 * x / args.steps for x in LAST_WALL],
                               h2d_bytes_per_step=int(sum(v.numel() * 4 for k, v in wl.pinned.items() if k != "features")),
                               d2h_bytes_per_step=4 + 4)
     train = None
@@ -912,7 +928,8 @@ def run_reference(args, rank, world, local):
                     note="unmodified reference CUDA rasterizer (diff-gaussian-rasterization) built for sm_100a, torch-free shim; "
                          "the reference has no distributed path: it runs on rank 0's GPU only, whatever N is"),
         e2e=dict(value=args.steps / e2e_sec, unit="views/s", ms_per_step=1000.0 * e2e_sec / args.steps,
-                 h2d_bytes_per_step=wl.h2d_bytes, d2h_bytes_per_step=4 + 4 * calls),
+                 h2d_bytes_per_step=wl.h2d_bytes, d2h_bytes_per_step=4 + 4 * calls, ms_per_step_blocks=e2e_blocks,
+                 timing=f"median of {E2E_REPEATS} back-to-back blocks of exactly `steps` steps on the host clock, each bracketed by barrier + synchronize"),
         gpu_launches=0, clocks=clocks, vanilla=vanilla, train=train,
         cpu_baseline=dict(value=None, unit="views/s", cores=0, kind="reference",
                           sample="the reference path is CUDA-only: this arm runs its own kernels on the B200, not a CPU port"),
