@@ -152,3 +152,28 @@ def test_reference_arm_of_the_bench_never_imports_the_product_library():
             "print('libb200gs' in open('/proc/self/maps').read())" % os.path.join(helpers.ROOT, "sdp-gs_b200"))
     out = subprocess.run([_sys.executable, "-c", code], stdout=subprocess.PIPE, text=True, check=True).stdout.strip()
     assert out == "False"
+
+
+def test_image_workspace_holds_the_cost_history_and_the_backward_order():
+    """ImageState carries, per tile, two cost words and a second launch order (persistent workspaces): the size query must
+    cover them (3 extra words per tile on top of ranges, order, counters and the two per-pixel planes)."""
+    from b200gs._lib import lib
+    W, H = 504, 378
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    assert lib.b200gs_image_bytes(W, H) >= 8 * W * H + (8 + 4 + 3 * 4) * tiles
+    assert lib.b200gs_image_bytes(W, H) % 256 == 0
+
+
+def test_gaussians_struct_ends_with_the_live_count_pointer():
+    from b200gs import _lib
+    names = [f[0] for f in _lib.Gaussians._fields_]
+    assert names[0] == "P" and names[-1] == "live_count"
+    g = _lib.Gaussians()
+    assert not g.live_count  # NULL: every row is a Gaussian (the reference's behaviour)
+
+
+def test_small_gaussian_counts_get_more_scan_tiles():
+    """geom workspace sizing follows the scan/emit CTA size: 256 Gaussians per CTA up to 32768, 1024 above."""
+    from b200gs._lib import lib
+    sizes = [lib.b200gs_geom_bytes(P) for P in (1000, 32768, 32769, 100000)]
+    assert all(b > a for a, b in zip(sizes, sizes[1:]))
